@@ -1,0 +1,188 @@
+/*
+ * lorab200.h -- C ABI of the B200-native LoRa demodulator hot path.
+ *
+ * This is the drop-in boundary: a Pothos::Block::work() (or any other host,
+ * via ctypes / cgo / JNI) calls these entry points instead of running the
+ * reference's scalar loop
+ *
+ *     for i < N: decd = in[i]*chirp[i](*fine[idx]); detector.feed(i, decd)   LoRaDemod.cpp:157-166
+ *     value = detector.detect(power, powerAvg, fIndex, fftBuff)             LoRaDemod.cpp:172
+ *         -> kissfft<float>::transform                                      LoRaDetector.hpp:32, kissfft.hh:77-157
+ *         -> |bin|^2 scan, first-max argmax, dB metrics, fractional index   LoRaDetector.hpp:33-61
+ *
+ * for a whole batch of symbol windows in ONE fused sm_100a kernel launch.
+ * All file:line citations are relative to the reference tree (myriadrf/LoRa-SDR).
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types; never throws.
+ *   - every function returns LORAB200_OK (0) or a negative lorab200_status;
+ *     lorab200_strerror() names it, lorab200_last_error() adds detail.
+ *   - the caller owns every buffer it passes; the library never retains a
+ *     caller pointer past the call (Pothos port buffers are only valid inside
+ *     work(), SURVEY.md section 8b "Ownership").
+ *   - a context is NOT thread-safe; distinct contexts are independent (one per
+ *     Pothos block instance / per channel), each with its own CUDA stream.
+ *   - complex samples are interleaved float32 pairs (re, im), i.e. the memory
+ *     layout of std::complex<float> (input port 0 dtype, LoRaDemod.cpp:79).
+ *   - there is NO CPU fallback: without a CUDA device lorab200_create fails
+ *     with LORAB200_ERR_CUDA.
+ */
+#ifndef LORAB200_H
+#define LORAB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LORAB200_ABI_VERSION 1
+
+typedef struct lorab200_ctx lorab200_ctx;
+
+typedef enum {
+    LORAB200_OK = 0,
+    LORAB200_ERR_INVALID = -1,   /* bad argument (sf out of 7..12, null pointer, ...) */
+    LORAB200_ERR_CUDA = -2,      /* CUDA runtime error / no device; see lorab200_last_error */
+    LORAB200_ERR_NOMEM = -3,     /* host or device allocation failed */
+    LORAB200_ERR_UNSUPPORTED = -4
+} lorab200_status;
+
+/* Which dechirp table a call multiplies by. LoRaDemod keeps two and switches
+ * with the frame-sync state (LoRaDemod.cpp:142,210,253). */
+typedef enum {
+    LORAB200_TABLE_UP = 0,    /* _upChirpTable: conj of the up-chirp   LoRaDemod.cpp:104 */
+    LORAB200_TABLE_DOWN = 1,  /* _downChirpTable                       LoRaDemod.cpp:105 */
+    LORAB200_TABLE_FINE = 2,  /* _fineTuneTable, N*128 entries         LoRaDemod.cpp:108-114 */
+    LORAB200_TABLE_TWIDDLE = 3/* kissfft twiddles, N entries           kissfft.hh:17-22 */
+} lorab200_table;
+
+/* One result per symbol window = the outputs of LoRaDetector::detect
+ * (LoRaDetector.hpp:29-64).  16 bytes, written once per window. */
+typedef struct {
+    int32_t index;      /* argmax bin, first maximum wins (strict >, init 0)  LoRaDetector.hpp:33-48 */
+    float   power;      /* 20*log10(sqrt(max|bin|^2)) - 20*log10(N)           LoRaDetector.hpp:18,54 */
+    float   power_avg;  /* 20*log10(sqrt(total - max)) - 20*log10(N)          LoRaDetector.hpp:50,53 */
+    float   f_index;    /* 0.5*(right-left)/(2*peak-right-left), 0 if denom==0 LoRaDetector.hpp:56-61 */
+} lorab200_result;
+
+/* Fine-tune state of the dechirp loop, LoRaDemod.cpp:159-162.
+ *   index  in : _fineTuneIndex at the first sample of window 0
+ *          out: its value after the last sample of the last window
+ *   step      : _finefreqError * _fineSteps, as a float (the amount the int
+ *               index is decremented by per sample, in float arithmetic).
+ * The recurrence advances over the N processed samples of every window, in
+ * window order, regardless of `stride_samples`.  Pass NULL for the
+ * TestDetector.cpp:25 form (single multiply by the chirp table, no fine table). */
+typedef struct {
+    int32_t index;
+    float   step;
+} lorab200_fine;
+
+/* Flags for lorab200_create. */
+#define LORAB200_FLAG_DEFAULT      0u
+#define LORAB200_FLAG_SIMPLE_ONLY  1u  /* force the simple one-stage-per-sync kernel (debug / cross-check) */
+
+/* ---- lifetime -------------------------------------------------------------- */
+
+/* Create a demod context for spreading factor sf (7..12, N = 2^sf samples per
+ * window) on CUDA device `device`.  Builds the reference's tables on the host
+ * with the reference's recipes (LoRaDemod.cpp:97-114, kissfft.hh:17-22) and
+ * uploads them.  Replaces: LoRaDemod::LoRaDemod + LoRaDetector ctor + kissfft
+ * ctor (LoRaDemod.cpp:68-117, LoRaDetector.hpp:12-20, kissfft.hh:71-75). */
+int lorab200_create(lorab200_ctx **ctx, int device, int sf, uint32_t flags);
+void lorab200_destroy(lorab200_ctx *ctx);
+
+int lorab200_sf(const lorab200_ctx *ctx);           /* spreading factor */
+size_t lorab200_n(const lorab200_ctx *ctx);         /* samples per window, 2^sf */
+int lorab200_device(const lorab200_ctx *ctx);
+
+/* ---- tables ---------------------------------------------------------------- */
+
+/* Read-only view of the host copy of a table (interleaved complex64).
+ * *n_complex receives the entry count. Pointer is valid until destroy/set. */
+const float *lorab200_table_host(const lorab200_ctx *ctx, int which, size_t *n_complex);
+
+/* Device pointer of a table (for an NCCL broadcast or inspection). */
+void *lorab200_table_dev(const lorab200_ctx *ctx, int which, size_t *n_complex);
+
+/* Replace the UP or DOWN dechirp table with caller-supplied values (N complex64,
+ * host memory), e.g. genChirp's down-chirp as TestDetector.cpp:14 uses. */
+int lorab200_set_table(lorab200_ctx *ctx, int which, const float *host_data);
+
+/* Re-read every table from DEVICE memory into the host mirror and the kernel's
+ * per-launch constants (call after overwriting table_dev() buffers, e.g. by an
+ * NCCL broadcast from rank 0). */
+int lorab200_tables_sync_from_dev(lorab200_ctx *ctx);
+
+/* Build one of the reference tables on the HOST into caller memory, without a
+ * context or a GPU (the recipe lorab200_create uses): `out` receives
+ * lorab200_table_len(sf, which) interleaved complex64 entries. */
+size_t lorab200_table_len(int sf, int which);
+int lorab200_build_table(int sf, int which, float *out);
+
+/* ChirpGenerator.hpp:21-47 genChirp<float> on the host (bit-identical recipe);
+ * the signal generator the modulator and TestDetector use.  Returns the number
+ * of samples generated (NN), or a negative status. */
+int lorab200_gen_chirp(float *samps, int N, int ovs, int NN, float f0, int down,
+                       float ampl, float *phase_accum);
+
+/* ---- the hot path ---------------------------------------------------------- */
+
+/*
+ * Demodulate n_windows symbol windows that are already in DEVICE memory.
+ *
+ *   iq_dev         device pointer, complex64; window w starts at sample
+ *                  w*stride_samples.  8-byte alignment is sufficient; 16-byte
+ *                  aligned dense input (stride == N) takes the TMA path.
+ *   table          LORAB200_TABLE_UP or LORAB200_TABLE_DOWN
+ *   fine           NULL, or in/out fine-tune state (host pointer)
+ *   out_dev        device pointer, n_windows lorab200_result records
+ *   fft_dev        NULL or device pointer, n_windows*N complex64: the FFT
+ *                  output of every window ("fft" debug port, LoRaDemod.cpp:172,324)
+ *   dec_dev        NULL or device pointer, n_windows*N complex64: the dechirped
+ *                  samples ("dec" debug port, LoRaDemod.cpp:164)
+ *   cuda_stream    cudaStream_t to launch on, or NULL for the context's stream.
+ *                  The call is asynchronous with respect to the host.
+ *
+ * Replaces LoRaDemod.cpp:157-172 (and its twin :192-203) for a whole batch.
+ */
+int lorab200_demod_dev(lorab200_ctx *ctx, const void *iq_dev, size_t n_windows,
+                       size_t stride_samples, int table, lorab200_fine *fine,
+                       lorab200_result *out_dev, void *fft_dev, void *dec_dev,
+                       void *cuda_stream);
+
+/*
+ * Same, with HOST buffers: copies the IQ span to the device, launches, copies
+ * results (and the optional fft/dec dumps) back, and synchronises.  This is
+ * the call a Pothos::Block::work() makes with its port buffers.  Pinned
+ * (page-locked) host memory makes the copies asynchronous and faster but is
+ * not required.
+ */
+int lorab200_demod_host(lorab200_ctx *ctx, const float *iq, size_t n_windows,
+                        size_t stride_samples, int table, lorab200_fine *fine,
+                        lorab200_result *out, float *fft, float *dec);
+
+/* Page-locked host memory for the buffers handed to lorab200_demod_host (what a
+ * block's custom BufferManager, LoRaDemod.cpp:330-358, would allocate from):
+ * pinned memory lets the H2D/D2H copies run at full PCIe rate.  NULL on failure. */
+void *lorab200_alloc_pinned(size_t bytes);
+void lorab200_free_pinned(void *p);
+
+/* Pack results into the wire format of the demod's output packet: one int16
+ * per symbol (LoRaDemod.cpp:260,290: _outSymbols.as<int16_t*>()[n] = int16_t(value)). */
+void lorab200_pack_symbols(const lorab200_result *results, size_t n, int16_t *symbols);
+
+/* ---- diagnostics ----------------------------------------------------------- */
+
+const char *lorab200_strerror(int status);
+const char *lorab200_last_error(const lorab200_ctx *ctx); /* "" if none; ctx may be NULL for create errors */
+unsigned long long lorab200_kernel_launches(const lorab200_ctx *ctx); /* kernels launched by this ctx so far */
+const char *lorab200_last_kernel(const lorab200_ctx *ctx);            /* name of the kernel variant last launched */
+int lorab200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LORAB200_H */

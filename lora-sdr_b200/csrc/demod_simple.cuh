@@ -1,0 +1,132 @@
+// demod_simple.cuh -- the plain kernel: one CTA per symbol window, the window in
+// shared memory, kissfft's in-place stages executed literally (one
+// __syncthreads per stage).  It is the general-purpose path: any stride /
+// alignment, the fine-tune recurrence with a non-zero step, the fft/dec debug
+// dumps.  The fused persistent kernel (demod_fused.cuh) is the fast path and
+// is cross-checked against this one on the GPU.
+//
+// Replaces, per window: LoRaDemod.cpp:157-166 (dechirp) + LoRaDetector.hpp:29-64
+// (FFT + scan) with kissfft.hh:83-157 as the FFT.
+#pragma once
+#include "common.cuh"
+
+namespace lorab200 {
+
+// kissfft's load permutation for N = 2^SF (kissfft.hh:90-94,101-103): output
+// slot j with mixed-radix digits (q_0 most significant) reads in[q_0 + r_0*(q_1 + ...)].
+// Radices are 4,...,4 and a final 2 when SF is odd (kissfft.hh:34-51).
+template <int SF>
+__device__ __forceinline__ int kiss_input_index(int j)
+{
+    constexpr int L4 = SF / 2;      // number of radix-4 stages
+    int i = 0, w = 1;
+    // digit s (s = 0 is the most significant digit of j)
+    int shift = SF;
+#pragma unroll
+    for (int s = 0; s < L4; ++s) {
+        shift -= 2;
+        i += ((j >> shift) & 3) * w;
+        w <<= 2;
+    }
+    if (SF & 1) i += (j & 1) * w;
+    return i;
+}
+
+constexpr int kSimpleThreads = 128;
+
+template <int SF>
+__global__ void __launch_bounds__(kSimpleThreads)
+demod_simple_kernel(const DemodParams p)
+{
+    constexpr int N = 1 << SF;
+    constexpr int T = kSimpleThreads;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *F = reinterpret_cast<float2 *>(smem_raw);          // N bins
+    int *fidx = reinterpret_cast<int *>(F + N);                // N fine indices (only if needed)
+    __shared__ float s_val[T / 32];
+    __shared__ int s_idx[T / 32];
+    __shared__ double s_sum[T / 32];
+
+    const int tid = threadIdx.x;
+    for (unsigned long long w = blockIdx.x; w < p.n_windows; w += gridDim.x) {
+        const float2 *in = p.iq + w * p.stride;
+        const bool fine = p.fine != nullptr;
+        const bool walk = fine && p.fine_step != 0.0f;
+        if (walk) {
+            // sequential recurrence over the window (LoRaDemod.cpp:160-162)
+            if (tid == 0) {
+                int idx = p.fine_idx0[w];
+                for (int i = 0; i < N; ++i) { fidx[i] = idx; idx = fine_next(idx, p.fine_step, p.fine_len); }
+            }
+            __syncthreads();
+        }
+        const int idx_const = fine ? p.fine_idx0[w] : 0;
+
+        // dechirp + digit-reversed load
+        for (int j = tid; j < N; j += T) {
+            const int i = kiss_input_index<SF>(j);
+            float2 d = cx_mul(in[i], p.chirp[i]);
+            if (fine) d = cx_mul(d, p.fine[walk ? fidx[i] : idx_const]);
+            if (p.dec) p.dec[w * N + i] = d;
+            F[j] = d;
+        }
+
+        // stages, deepest first: radix-2 (odd SF) with m=1, then radix-4 with m=..,
+        int m = 1;
+        if (SF & 1) {
+            __syncthreads();
+            for (int b = tid; b < N / 2; b += T) {
+                float2 a0 = F[2 * b], a1 = cx_mul(F[2 * b + 1], p.tw[0]);
+                bfly2(a0, a1);
+                F[2 * b] = a0; F[2 * b + 1] = a1;
+            }
+            m = 2;
+        }
+        for (; m < N; m <<= 2) {
+            __syncthreads();
+            const int fstride = N / (4 * m);
+            for (int b = tid; b < N / 4; b += T) {
+                const int k = b & (m - 1);
+                const int base = (b - k) * 4 + k;
+                float2 a0 = F[base];
+                float2 a1 = cx_mul(F[base + m], p.tw[k * fstride]);
+                float2 a2 = cx_mul(F[base + 2 * m], p.tw[2 * k * fstride]);
+                float2 a3 = cx_mul(F[base + 3 * m], p.tw[3 * k * fstride]);
+                bfly4(a0, a1, a2, a3);
+                F[base] = a0; F[base + m] = a1; F[base + 2 * m] = a2; F[base + 3 * m] = a3;
+            }
+        }
+        __syncthreads();
+
+        // peak scan (LoRaDetector.hpp:33-48): strict '>' from 0, first max wins
+        float bv = 0.0f; int bi = 0; double sum = 0.0;
+        for (int j = tid; j < N; j += T) {
+            const float2 v = F[j];
+            if (p.fft) p.fft[w * N + j] = v;
+            const float m2 = cx_mag2(v);
+            sum += double(m2);
+            if (m2 > bv) { bv = m2; bi = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_down_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            sum += __shfl_down_sync(0xffffffffu, sum, o);
+            argmax_merge(bv, bi, ov, oi);
+        }
+        if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; s_sum[tid >> 5] = sum; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < T / 32; ++k) { argmax_merge(bv, bi, s_val[k], s_idx[k]); sum += s_sum[k]; }
+            RawResult r;
+            r.index = bi; r.max_mag2 = bv; r.total = sum;
+            r.left = F[bi > 0 ? bi - 1 : N - 1];
+            r.right = F[bi < N - 1 ? bi + 1 : 0];
+            if (p.raw) p.raw[w] = r;
+            if (p.out) finalize_device(r, p.power_scale, &p.out[w]);
+        }
+        __syncthreads();
+    }
+}
+
+} // namespace lorab200

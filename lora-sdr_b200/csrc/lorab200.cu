@@ -1,0 +1,425 @@
+// lorab200.cu -- context, C ABI (include/lorab200.h) and kernel dispatch.
+//
+// Host side of the drop-in boundary: everything a Pothos::Block::work() needs to
+// replace LoRaDemod.cpp:157-172 with one call.  No torch types, no exceptions
+// across the ABI, no CPU fallback: if CUDA is unavailable create() fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lorab200.h"
+#include "common.cuh"
+#include "demod_simple.cuh"
+#ifndef LORAB200_NO_FUSED
+#include "demod_fused.cuh"
+#endif
+#include "finalize.h"
+#include "tables.h"
+
+using namespace lorab200;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+} // namespace
+
+struct lorab200_ctx {
+    int device = 0;
+    int sf = 0;
+    size_t n = 0;
+    uint32_t flags = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::string last_kernel;
+    unsigned long long launches = 0;
+    float pscale = 0.0f;
+
+    std::vector<cfloat> h_table[4];
+    float2 *d_table[4] = {nullptr, nullptr, nullptr, nullptr};
+
+    // scratch for the host-buffer entry point and the fine-tune pre-roll
+    DevBuf d_iq, d_raw, d_fft, d_dec, d_idx0;
+    void *h_raw = nullptr;   // pinned
+    size_t h_raw_cap = 0;
+    void *h_idx0 = nullptr;  // pinned
+    size_t h_idx0_cap = 0;
+};
+
+namespace {
+
+int fail(lorab200_ctx *c, int status, const char *what, cudaError_t e = cudaSuccess)
+{
+    std::string m = what;
+    if (e != cudaSuccess) { m += ": "; m += cudaGetErrorString(e); }
+    if (c) c->err = m; else g_create_error = m;
+    return status;
+}
+
+#define CU_TRY(c, expr)                                                         \
+    do {                                                                        \
+        cudaError_t e__ = (expr);                                               \
+        if (e__ != cudaSuccess) return fail((c), LORAB200_ERR_CUDA, #expr, e__); \
+    } while (0)
+
+int ensure_dev(lorab200_ctx *c, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return LORAB200_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(c, LORAB200_ERR_NOMEM, "cudaMalloc(scratch)", e); }
+    b.cap = want;
+    return LORAB200_OK;
+}
+
+int ensure_pinned(lorab200_ctx *c, void *&p, size_t &cap, size_t bytes)
+{
+    if (bytes <= cap) return LORAB200_OK;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(c, LORAB200_ERR_NOMEM, "cudaMallocHost(scratch)", e); }
+    cap = want;
+    return LORAB200_OK;
+}
+
+int upload_table(lorab200_ctx *c, int which)
+{
+    const size_t bytes = c->h_table[which].size() * sizeof(cfloat);
+    if (!c->d_table[which]) CU_TRY(c, cudaMalloc(&c->d_table[which], bytes));
+    CU_TRY(c, cudaMemcpy(c->d_table[which], c->h_table[which].data(), bytes, cudaMemcpyHostToDevice));
+    return LORAB200_OK;
+}
+
+template <int SF>
+cudaError_t launch_simple_sf(const DemodParams &p, cudaStream_t s, int sm_count)
+{
+    constexpr int N = 1 << SF;
+    const size_t smem = size_t(N) * sizeof(float2) + size_t(N) * sizeof(int);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(demod_simple_kernel<SF>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    unsigned long long grid = p.n_windows;
+    const unsigned long long cap = (unsigned long long)sm_count * 64ull;
+    if (grid > cap) grid = cap; // grid-stride over windows
+    demod_simple_kernel<SF><<<unsigned(grid), kSimpleThreads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_simple(int sf, const DemodParams &p, cudaStream_t s, int sm_count)
+{
+    switch (sf) {
+    case 7: return launch_simple_sf<7>(p, s, sm_count);
+    case 8: return launch_simple_sf<8>(p, s, sm_count);
+    case 9: return launch_simple_sf<9>(p, s, sm_count);
+    case 10: return launch_simple_sf<10>(p, s, sm_count);
+    case 11: return launch_simple_sf<11>(p, s, sm_count);
+    case 12: return launch_simple_sf<12>(p, s, sm_count);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+// Pre-roll the fine-tune index recurrence (LoRaDemod.cpp:160-162) to the start
+// of every window; sequential by nature, O(N*W) integer/float steps on the host.
+void roll_fine(int32_t idx, float step, int32_t len, size_t n, size_t n_windows,
+               int32_t *idx0, int32_t *idx_end)
+{
+    for (size_t w = 0; w < n_windows; ++w) {
+        idx0[w] = idx;
+        if (step != 0.0f) {
+            for (size_t i = 0; i < n; ++i) {
+                idx = int32_t(float(idx) - step);
+                if (idx < 0) idx += len;
+                else if (idx >= len) idx -= len;
+            }
+        }
+    }
+    *idx_end = idx;
+}
+
+// Common launch path. `results`/`raw` are device pointers (exactly one non-null).
+int run_demod(lorab200_ctx *c, const void *iq_dev, size_t n_windows, size_t stride, int table,
+              lorab200_fine *fine, lorab200_result *out_dev, RawResult *raw_dev, void *fft_dev,
+              void *dec_dev, cudaStream_t s)
+{
+    if (table != LORAB200_TABLE_UP && table != LORAB200_TABLE_DOWN)
+        return fail(c, LORAB200_ERR_INVALID, "table must be LORAB200_TABLE_UP or LORAB200_TABLE_DOWN");
+    if (n_windows == 0) return LORAB200_OK;
+    if (!iq_dev) return fail(c, LORAB200_ERR_INVALID, "iq pointer is null");
+    if (!out_dev && !raw_dev) return fail(c, LORAB200_ERR_INVALID, "output pointer is null");
+    if ((reinterpret_cast<uintptr_t>(iq_dev) & 7u) != 0)
+        return fail(c, LORAB200_ERR_INVALID, "iq pointer must be 8-byte aligned");
+    if (n_windows > 1 && stride == 0) return fail(c, LORAB200_ERR_INVALID, "stride_samples must be > 0");
+
+    DemodParams p{};
+    p.iq = static_cast<const float2 *>(iq_dev);
+    p.n_windows = n_windows;
+    p.stride = stride;
+    p.chirp = c->d_table[table];
+    p.tw = c->d_table[LORAB200_TABLE_TWIDDLE];
+    p.power_scale = c->pscale;
+    p.out = out_dev;
+    p.raw = raw_dev;
+    p.fft = static_cast<float2 *>(fft_dev);
+    p.dec = static_cast<float2 *>(dec_dev);
+    p.fine_len = int(c->n * kFineSteps);
+
+    if (fine) {
+        if (fine->index < 0 || fine->index >= p.fine_len)
+            return fail(c, LORAB200_ERR_INVALID, "fine->index out of [0, N*128)");
+        int st = ensure_pinned(c, c->h_idx0, c->h_idx0_cap, n_windows * sizeof(int32_t));
+        if (st) return st;
+        st = ensure_dev(c, c->d_idx0, n_windows * sizeof(int32_t));
+        if (st) return st;
+        int32_t end = fine->index;
+        roll_fine(fine->index, fine->step, p.fine_len, c->n, n_windows, static_cast<int32_t *>(c->h_idx0), &end);
+        CU_TRY(c, cudaMemcpyAsync(c->d_idx0.p, c->h_idx0, n_windows * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        // h_idx0 is reused by the next call: make sure the copy has left the host buffer
+        CU_TRY(c, cudaStreamSynchronize(s));
+        fine->index = end;
+        p.fine = c->d_table[LORAB200_TABLE_FINE];
+        p.fine_idx0 = static_cast<const int32_t *>(c->d_idx0.p);
+        p.fine_step = fine->step;
+    }
+
+    cudaError_t e;
+#ifndef LORAB200_NO_FUSED
+    if (!(c->flags & LORAB200_FLAG_SIMPLE_ONLY) && fused_applicable(c->sf, p)) {
+        e = launch_fused(c->sf, p, s, c->sm_count);
+        c->last_kernel = std::string("fused_sf") + std::to_string(c->sf);
+    } else
+#endif
+    {
+        e = launch_simple(c->sf, p, s, c->sm_count);
+        c->last_kernel = std::string("simple_sf") + std::to_string(c->sf);
+    }
+    if (e != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "kernel launch", e);
+    c->launches++;
+    return LORAB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int lorab200_abi_version(void) { return LORAB200_ABI_VERSION; }
+
+const char *lorab200_strerror(int status)
+{
+    switch (status) {
+    case LORAB200_OK: return "ok";
+    case LORAB200_ERR_INVALID: return "invalid argument";
+    case LORAB200_ERR_CUDA: return "CUDA error";
+    case LORAB200_ERR_NOMEM: return "out of memory";
+    case LORAB200_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown status";
+    }
+}
+
+const char *lorab200_last_error(const lorab200_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int lorab200_create(lorab200_ctx **out, int device, int sf, uint32_t flags)
+{
+    if (!out) return fail(nullptr, LORAB200_ERR_INVALID, "ctx out-pointer is null");
+    *out = nullptr;
+    if (sf < 7 || sf > 12) return fail(nullptr, LORAB200_ERR_INVALID, "sf must be in 7..12");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(nullptr, LORAB200_ERR_CUDA, "no CUDA device (this library has no CPU fallback)", e);
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, LORAB200_ERR_INVALID, "device index out of range");
+    lorab200_ctx *c = new (std::nothrow) lorab200_ctx();
+    if (!c) return fail(nullptr, LORAB200_ERR_NOMEM, "ctx allocation");
+    c->device = device;
+    c->sf = sf;
+    c->n = size_t(1) << sf;
+    c->flags = flags;
+    c->pscale = power_scale(sf);
+    int st = LORAB200_OK;
+    do {
+        if ((e = cudaSetDevice(device)) != cudaSuccess) { st = fail(nullptr, LORAB200_ERR_CUDA, "cudaSetDevice", e); break; }
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { st = fail(nullptr, LORAB200_ERR_CUDA, "cudaGetDeviceProperties", e); break; }
+        if (prop.major != 10) { st = fail(nullptr, LORAB200_ERR_UNSUPPORTED, "device is not sm_100 (B200); kernels are built for sm_100a only"); break; }
+        c->sm_count = prop.multiProcessorCount;
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { st = fail(nullptr, LORAB200_ERR_CUDA, "cudaStreamCreate", e); break; }
+        build_dechirp_tables(sf, c->h_table[LORAB200_TABLE_UP], c->h_table[LORAB200_TABLE_DOWN]);
+        build_fine_table(sf, c->h_table[LORAB200_TABLE_FINE]);
+        build_twiddles(sf, c->h_table[LORAB200_TABLE_TWIDDLE]);
+        for (int t = 0; t < 4 && st == LORAB200_OK; ++t) {
+            st = upload_table(c, t);
+            if (st) g_create_error = c->err;
+        }
+    } while (0);
+    if (st != LORAB200_OK) { lorab200_destroy(c); return st; }
+    *out = c;
+    return LORAB200_OK;
+}
+
+void lorab200_destroy(lorab200_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (auto &t : c->d_table) if (t) cudaFree(t);
+    for (DevBuf *b : {&c->d_iq, &c->d_raw, &c->d_fft, &c->d_dec, &c->d_idx0}) if (b->p) cudaFree(b->p);
+    if (c->h_raw) cudaFreeHost(c->h_raw);
+    if (c->h_idx0) cudaFreeHost(c->h_idx0);
+    (void)cudaGetLastError();
+    delete c;
+}
+
+int lorab200_sf(const lorab200_ctx *c) { return c ? c->sf : LORAB200_ERR_INVALID; }
+size_t lorab200_n(const lorab200_ctx *c) { return c ? c->n : 0; }
+int lorab200_device(const lorab200_ctx *c) { return c ? c->device : LORAB200_ERR_INVALID; }
+unsigned long long lorab200_kernel_launches(const lorab200_ctx *c) { return c ? c->launches : 0; }
+const char *lorab200_last_kernel(const lorab200_ctx *c) { return c ? c->last_kernel.c_str() : ""; }
+
+const float *lorab200_table_host(const lorab200_ctx *c, int which, size_t *n_complex)
+{
+    if (!c || which < 0 || which > 3) return nullptr;
+    if (n_complex) *n_complex = c->h_table[which].size();
+    return reinterpret_cast<const float *>(c->h_table[which].data());
+}
+
+void *lorab200_table_dev(const lorab200_ctx *c, int which, size_t *n_complex)
+{
+    if (!c || which < 0 || which > 3) return nullptr;
+    if (n_complex) *n_complex = c->h_table[which].size();
+    return c->d_table[which];
+}
+
+int lorab200_set_table(lorab200_ctx *c, int which, const float *host_data)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    if (which != LORAB200_TABLE_UP && which != LORAB200_TABLE_DOWN)
+        return fail(c, LORAB200_ERR_INVALID, "only the UP / DOWN dechirp tables can be replaced");
+    if (!host_data) return fail(c, LORAB200_ERR_INVALID, "host_data is null");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(c->h_table[which].data(), host_data, c->n * sizeof(cfloat));
+    return upload_table(c, which);
+}
+
+int lorab200_tables_sync_from_dev(lorab200_ctx *c)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaDeviceSynchronize());
+    for (int t = 0; t < 4; ++t)
+        CU_TRY(c, cudaMemcpy(c->h_table[t].data(), c->d_table[t], c->h_table[t].size() * sizeof(cfloat),
+                             cudaMemcpyDeviceToHost));
+    return LORAB200_OK;
+}
+
+size_t lorab200_table_len(int sf, int which)
+{
+    if (sf < 7 || sf > 12 || which < 0 || which > 3) return 0;
+    const size_t n = size_t(1) << sf;
+    return which == LORAB200_TABLE_FINE ? n * kFineSteps : n;
+}
+
+int lorab200_build_table(int sf, int which, float *out)
+{
+    if (!out || lorab200_table_len(sf, which) == 0) return LORAB200_ERR_INVALID;
+    std::vector<cfloat> a, b;
+    switch (which) {
+    case LORAB200_TABLE_UP: build_dechirp_tables(sf, a, b); break;
+    case LORAB200_TABLE_DOWN: build_dechirp_tables(sf, b, a); break;
+    case LORAB200_TABLE_FINE: build_fine_table(sf, a); break;
+    default: build_twiddles(sf, a); break;
+    }
+    std::memcpy(out, a.data(), a.size() * sizeof(cfloat));
+    return LORAB200_OK;
+}
+
+int lorab200_gen_chirp(float *samps, int N, int ovs, int NN, float f0, int down, float ampl,
+                       float *phase_accum)
+{
+    if (!samps || !phase_accum || N <= 0 || ovs <= 0 || NN < 0) return LORAB200_ERR_INVALID;
+    return gen_chirp(reinterpret_cast<cfloat *>(samps), N, ovs, NN, f0, down != 0, ampl, *phase_accum);
+}
+
+int lorab200_demod_dev(lorab200_ctx *c, const void *iq_dev, size_t n_windows, size_t stride_samples,
+                       int table, lorab200_fine *fine, lorab200_result *out_dev, void *fft_dev,
+                       void *dec_dev, void *cuda_stream)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    c->err.clear();
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream;
+    return run_demod(c, iq_dev, n_windows, stride_samples, table, fine, out_dev, nullptr, fft_dev, dec_dev, s);
+}
+
+int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size_t stride_samples,
+                        int table, lorab200_fine *fine, lorab200_result *out, float *fft, float *dec)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    c->err.clear();
+    if (n_windows == 0) return LORAB200_OK;
+    if (!iq || !out) return fail(c, LORAB200_ERR_INVALID, "iq / out pointer is null");
+    if (n_windows > 1 && stride_samples == 0) return fail(c, LORAB200_ERR_INVALID, "stride_samples must be > 0");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t n = c->n;
+    const size_t span = (n_windows - 1) * stride_samples + n; // samples touched
+    const size_t dump = n_windows * n * sizeof(float2);
+    int st;
+    if ((st = ensure_dev(c, c->d_iq, span * sizeof(float2)))) return st;
+    if ((st = ensure_dev(c, c->d_raw, n_windows * sizeof(RawResult)))) return st;
+    if ((st = ensure_pinned(c, c->h_raw, c->h_raw_cap, n_windows * sizeof(RawResult)))) return st;
+    if (fft && (st = ensure_dev(c, c->d_fft, dump))) return st;
+    if (dec && (st = ensure_dev(c, c->d_dec, dump))) return st;
+
+    CU_TRY(c, cudaMemcpyAsync(c->d_iq.p, iq, span * sizeof(float2), cudaMemcpyHostToDevice, s));
+    st = run_demod(c, c->d_iq.p, n_windows, stride_samples, table, fine, nullptr,
+                   static_cast<RawResult *>(c->d_raw.p), fft ? c->d_fft.p : nullptr,
+                   dec ? c->d_dec.p : nullptr, s);
+    if (st) return st;
+    CU_TRY(c, cudaMemcpyAsync(c->h_raw, c->d_raw.p, n_windows * sizeof(RawResult), cudaMemcpyDeviceToHost, s));
+    if (fft) CU_TRY(c, cudaMemcpyAsync(fft, c->d_fft.p, dump, cudaMemcpyDeviceToHost, s));
+    if (dec) CU_TRY(c, cudaMemcpyAsync(dec, c->d_dec.p, dump, cudaMemcpyDeviceToHost, s));
+    CU_TRY(c, cudaStreamSynchronize(s));
+    finalize_host(static_cast<const RawResultHost *>(c->h_raw), n_windows, c->pscale, out);
+    return LORAB200_OK;
+}
+
+void *lorab200_alloc_pinned(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void lorab200_free_pinned(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+void lorab200_pack_symbols(const lorab200_result *results, size_t n, int16_t *symbols)
+{
+    if (!results || !symbols) return;
+    for (size_t i = 0; i < n; ++i) symbols[i] = int16_t(results[i].index);
+}
+
+} // extern "C"
