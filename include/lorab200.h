@@ -143,8 +143,10 @@ int lorab200_gen_chirp(float *samps, int N, int ovs, int NN, float f0, int down,
  *                  output of every window ("fft" debug port, LoRaDemod.cpp:172,324)
  *   dec_dev        NULL or device pointer, n_windows*N complex64: the dechirped
  *                  samples ("dec" debug port, LoRaDemod.cpp:164)
- *   cuda_stream    cudaStream_t to launch on, or NULL for the context's stream.
- *                  The call is asynchronous with respect to the host.
+ *   cuda_stream    cudaStream_t to launch on; NULL is CUDA's default stream
+ *                  (the usual CUDA convention, and what torch's default stream
+ *                  is).  The call is asynchronous with respect to the host;
+ *                  work is ordered with whatever else is on that stream.
  *
  * Replaces LoRaDemod.cpp:157-172 (and its twin :192-203) for a whole batch.
  */

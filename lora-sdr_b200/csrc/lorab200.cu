@@ -47,6 +47,9 @@ struct lorab200_ctx {
 
     std::vector<cfloat> h_table[4];
     float2 *d_table[4] = {nullptr, nullptr, nullptr, nullptr};
+#ifndef LORAB200_NO_FUSED
+    Pass0Tw tw0;             // uniform pass-0 twiddles of the fused kernel (kernel parameter)
+#endif
 
     // scratch for the host-buffer entry point and the fine-tune pre-roll
     DevBuf d_iq, d_raw, d_fft, d_dec, d_idx0;
@@ -99,6 +102,10 @@ int upload_table(lorab200_ctx *c, int which)
     const size_t bytes = c->h_table[which].size() * sizeof(cfloat);
     if (!c->d_table[which]) CU_TRY(c, cudaMalloc(&c->d_table[which], bytes));
     CU_TRY(c, cudaMemcpy(c->d_table[which], c->h_table[which].data(), bytes, cudaMemcpyHostToDevice));
+#ifndef LORAB200_NO_FUSED
+    if (which == LORAB200_TABLE_TWIDDLE)
+        fill_pass0_tw(c->sf, reinterpret_cast<const float2 *>(c->h_table[which].data()), c->tw0);
+#endif
     return LORAB200_OK;
 }
 
@@ -200,7 +207,7 @@ int run_demod(lorab200_ctx *c, const void *iq_dev, size_t n_windows, size_t stri
     cudaError_t e;
 #ifndef LORAB200_NO_FUSED
     if (!(c->flags & LORAB200_FLAG_SIMPLE_ONLY) && fused_applicable(c->sf, p)) {
-        e = launch_fused(c->sf, p, s, c->sm_count);
+        e = launch_fused(c->sf, p, c->tw0, s, c->sm_count);
         c->last_kernel = std::string("fused_sf") + std::to_string(c->sf);
     } else
 #endif
@@ -329,6 +336,9 @@ int lorab200_tables_sync_from_dev(lorab200_ctx *c)
     for (int t = 0; t < 4; ++t)
         CU_TRY(c, cudaMemcpy(c->h_table[t].data(), c->d_table[t], c->h_table[t].size() * sizeof(cfloat),
                              cudaMemcpyDeviceToHost));
+#ifndef LORAB200_NO_FUSED
+    fill_pass0_tw(c->sf, reinterpret_cast<const float2 *>(c->h_table[LORAB200_TABLE_TWIDDLE].data()), c->tw0);
+#endif
     return LORAB200_OK;
 }
 
@@ -367,7 +377,7 @@ int lorab200_demod_dev(lorab200_ctx *c, const void *iq_dev, size_t n_windows, si
     if (!c) return LORAB200_ERR_INVALID;
     c->err.clear();
     CU_TRY(c, cudaSetDevice(c->device));
-    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream); // NULL == CUDA default stream
     return run_demod(c, iq_dev, n_windows, stride_samples, table, fine, out_dev, nullptr, fft_dev, dec_dev, s);
 }
 
