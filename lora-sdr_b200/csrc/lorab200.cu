@@ -189,29 +189,38 @@ int run_demod(lorab200_ctx *c, const void *iq_dev, size_t n_windows, size_t stri
     if (fine) {
         if (fine->index < 0 || fine->index >= p.fine_len)
             return fail(c, LORAB200_ERR_INVALID, "fine->index out of [0, N*128)");
-        int st = ensure_pinned(c, c->h_idx0, c->h_idx0_cap, n_windows * sizeof(int32_t));
-        if (st) return st;
-        st = ensure_dev(c, c->d_idx0, n_windows * sizeof(int32_t));
-        if (st) return st;
-        int32_t end = fine->index;
-        roll_fine(fine->index, fine->step, p.fine_len, c->n, n_windows, static_cast<int32_t *>(c->h_idx0), &end);
-        CU_TRY(c, cudaMemcpyAsync(c->d_idx0.p, c->h_idx0, n_windows * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-        // h_idx0 is reused by the next call: make sure the copy has left the host buffer
-        CU_TRY(c, cudaStreamSynchronize(s));
-        fine->index = end;
         p.fine = c->d_table[LORAB200_TABLE_FINE];
-        p.fine_idx0 = static_cast<const int32_t *>(c->d_idx0.p);
         p.fine_step = fine->step;
     }
 
     cudaError_t e;
 #ifndef LORAB200_NO_FUSED
     if (!(c->flags & LORAB200_FLAG_SIMPLE_ONLY) && fused_applicable(c->sf, p)) {
-        e = launch_fused(c->sf, p, c->tw0, s, c->sm_count);
+        // fine-tune with a zero step: the index never moves (LoRaDemod.cpp:160 with
+        // _finefreqError == 0), so the whole batch is multiplied by one phasor
+        float2 phasor = make_float2(1.f, 0.f);
+        if (fine) {
+            const cfloat f = c->h_table[LORAB200_TABLE_FINE][size_t(fine->index)];
+            phasor = make_float2(f.re, f.im);
+        }
+        e = launch_fused(c->sf, p, c->tw0, fine != nullptr, phasor, s, c->sm_count);
         c->last_kernel = std::string("fused_sf") + std::to_string(c->sf);
     } else
 #endif
     {
+        if (fine) {
+            int st = ensure_pinned(c, c->h_idx0, c->h_idx0_cap, n_windows * sizeof(int32_t));
+            if (st) return st;
+            st = ensure_dev(c, c->d_idx0, n_windows * sizeof(int32_t));
+            if (st) return st;
+            int32_t end = fine->index;
+            roll_fine(fine->index, fine->step, p.fine_len, c->n, n_windows, static_cast<int32_t *>(c->h_idx0), &end);
+            CU_TRY(c, cudaMemcpyAsync(c->d_idx0.p, c->h_idx0, n_windows * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+            // h_idx0 is reused by the next call: make sure the copy has left the host buffer
+            CU_TRY(c, cudaStreamSynchronize(s));
+            fine->index = end;
+            p.fine_idx0 = static_cast<const int32_t *>(c->d_idx0.p);
+        }
         e = launch_simple(c->sf, p, s, c->sm_count);
         c->last_kernel = std::string("simple_sf") + std::to_string(c->sf);
     }
