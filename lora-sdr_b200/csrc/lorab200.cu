@@ -9,6 +9,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lorab200.h"
@@ -40,6 +41,8 @@ struct lorab200_ctx {
     uint32_t flags = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // second lane of the host-buffer pipeline
+    cudaEvent_t chunk_done[64] = {};          // D2H-complete events of the in-flight chunks
     std::string err;
     std::string last_kernel;
     unsigned long long launches = 0;
@@ -279,6 +282,10 @@ int lorab200_create(lorab200_ctx **out, int device, int sf, uint32_t flags)
         if (prop.major != 10) { st = fail(nullptr, LORAB200_ERR_UNSUPPORTED, "device is not sm_100 (B200); kernels are built for sm_100a only"); break; }
         c->sm_count = prop.multiProcessorCount;
         if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { st = fail(nullptr, LORAB200_ERR_CUDA, "cudaStreamCreate", e); break; }
+        if ((e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess) { st = fail(nullptr, LORAB200_ERR_CUDA, "cudaStreamCreate", e); break; }
+        for (auto &ev : c->chunk_done)
+            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) break;
+        if (e != cudaSuccess) { st = fail(nullptr, LORAB200_ERR_CUDA, "cudaEventCreate", e); break; }
         build_dechirp_tables(sf, c->h_table[LORAB200_TABLE_UP], c->h_table[LORAB200_TABLE_DOWN]);
         build_fine_table(sf, c->h_table[LORAB200_TABLE_FINE]);
         build_twiddles(sf, c->h_table[LORAB200_TABLE_TWIDDLE]);
@@ -297,6 +304,8 @@ void lorab200_destroy(lorab200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    for (auto &ev : c->chunk_done) if (ev) cudaEventDestroy(ev);
     for (auto &t : c->d_table) if (t) cudaFree(t);
     for (DevBuf *b : {&c->d_iq, &c->d_raw, &c->d_fft, &c->d_dec, &c->d_idx0}) if (b->p) cudaFree(b->p);
     if (c->h_raw) cudaFreeHost(c->h_raw);
@@ -399,7 +408,6 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     if (!iq || !out) return fail(c, LORAB200_ERR_INVALID, "iq / out pointer is null");
     if (n_windows > 1 && stride_samples == 0) return fail(c, LORAB200_ERR_INVALID, "stride_samples must be > 0");
     CU_TRY(c, cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
     const size_t n = c->n;
     const size_t span = (n_windows - 1) * stride_samples + n; // samples touched
     const size_t dump = n_windows * n * sizeof(float2);
@@ -410,16 +418,77 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     if (fft && (st = ensure_dev(c, c->d_fft, dump))) return st;
     if (dec && (st = ensure_dev(c, c->d_dec, dump))) return st;
 
-    CU_TRY(c, cudaMemcpyAsync(c->d_iq.p, iq, span * sizeof(float2), cudaMemcpyHostToDevice, s));
-    st = run_demod(c, c->d_iq.p, n_windows, stride_samples, table, fine, nullptr,
-                   static_cast<RawResult *>(c->d_raw.p), fft ? c->d_fft.p : nullptr,
-                   dec ? c->d_dec.p : nullptr, s);
-    if (st) return st;
-    CU_TRY(c, cudaMemcpyAsync(c->h_raw, c->d_raw.p, n_windows * sizeof(RawResult), cudaMemcpyDeviceToHost, s));
-    if (fft) CU_TRY(c, cudaMemcpyAsync(fft, c->d_fft.p, dump, cudaMemcpyDeviceToHost, s));
-    if (dec) CU_TRY(c, cudaMemcpyAsync(dec, c->d_dec.p, dump, cudaMemcpyDeviceToHost, s));
-    CU_TRY(c, cudaStreamSynchronize(s));
-    finalize_host(static_cast<const RawResultHost *>(c->h_raw), n_windows, c->pscale, out);
+    // Software pipeline over chunks of windows on two streams: the H2D copy of chunk
+    // i+1 overlaps the kernel and the D2H copy of chunk i, and the host-side
+    // finalisation (libm) of chunk i-1.  A chunk is ~4 MiB of IQ, at most 64 chunks.
+    size_t cw = (size_t(4) << 20) / (n * sizeof(float2));
+    if (cw == 0) cw = 1;
+    if ((n_windows + cw - 1) / cw > 64) cw = (n_windows + 63) / 64;
+    // a walking fine-tune index is pre-rolled through per-context scratch: no pipelining
+    if (fine && fine->step != 0.0f) cw = n_windows;
+    const size_t n_chunks = (n_windows + cw - 1) / cw;
+    const float2 *h_iq = reinterpret_cast<const float2 *>(iq);
+    float2 *d_iq = static_cast<float2 *>(c->d_iq.p);
+    RawResult *d_raw = static_cast<RawResult *>(c->d_raw.p);
+    RawResultHost *h_raw = static_cast<RawResultHost *>(c->h_raw);
+    size_t copied_to = 0; // samples [0, copied_to) are already on the device
+    for (size_t k = 0; k < n_chunks; ++k) {
+        cudaStream_t s = (k & 1) ? c->stream2 : c->stream;
+        const size_t w0 = k * cw, w1 = (w0 + cw < n_windows) ? w0 + cw : n_windows, nw = w1 - w0;
+        const size_t s0 = w0 * stride_samples, s1 = (w1 - 1) * stride_samples + n; // sample range of the chunk
+        const size_t from = s0 > copied_to ? s0 : copied_to;                        // skip what an earlier chunk brought
+        if (s1 > from) {
+            // stride < N: the head of this chunk was copied by chunk k-1 on the other
+            // stream; order this stream after that chunk
+            if (k > 0 && from > s0) CU_TRY(c, cudaStreamWaitEvent(s, c->chunk_done[(k - 1) % 64], 0));
+            CU_TRY(c, cudaMemcpyAsync(d_iq + from, h_iq + from, (s1 - from) * sizeof(float2), cudaMemcpyHostToDevice, s));
+            copied_to = s1;
+        }
+        st = run_demod(c, d_iq + s0, nw, stride_samples, table, fine, nullptr, d_raw + w0,
+                       fft ? static_cast<float2 *>(c->d_fft.p) + w0 * n : nullptr,
+                       dec ? static_cast<float2 *>(c->d_dec.p) + w0 * n : nullptr, s);
+        if (st) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); return st; }
+        CU_TRY(c, cudaMemcpyAsync(h_raw + w0, d_raw + w0, nw * sizeof(RawResult), cudaMemcpyDeviceToHost, s));
+        if (fft) CU_TRY(c, cudaMemcpyAsync(reinterpret_cast<float2 *>(fft) + w0 * n, static_cast<float2 *>(c->d_fft.p) + w0 * n,
+                                           nw * n * sizeof(float2), cudaMemcpyDeviceToHost, s));
+        if (dec) CU_TRY(c, cudaMemcpyAsync(reinterpret_cast<float2 *>(dec) + w0 * n, static_cast<float2 *>(c->d_dec.p) + w0 * n,
+                                           nw * n * sizeof(float2), cudaMemcpyDeviceToHost, s));
+        CU_TRY(c, cudaEventRecord(c->chunk_done[k % 64], s));
+    }
+    // Host-side finalisation (libm log10f/hypotf, LoRaDetector.hpp:50-61) of chunk k as
+    // soon as its results have landed, while later chunks are still in flight.  Large
+    // batches split the chunks over a few threads so this stays hidden behind the H2D copy.
+    auto finish = [&](size_t first, size_t step) -> cudaError_t {
+        cudaSetDevice(c->device);
+        for (size_t k = first; k < n_chunks; k += step) {
+            cudaError_t e = cudaEventSynchronize(c->chunk_done[k % 64]);
+            if (e != cudaSuccess) return e;
+            const size_t p0 = k * cw, p1 = (p0 + cw < n_windows) ? p0 + cw : n_windows;
+            finalize_host(h_raw + p0, p1 - p0, c->pscale, out + p0);
+        }
+        return cudaSuccess;
+    };
+    size_t n_thr = 1;
+    if (n_windows >= 16384 && n_chunks >= 4) {
+        n_thr = std::thread::hardware_concurrency() / 4;
+        if (n_thr > 8) n_thr = 8;
+        if (n_thr > n_chunks) n_thr = n_chunks;
+        if (n_thr < 1) n_thr = 1;
+    }
+    cudaError_t ferr = cudaSuccess;
+    if (n_thr == 1) {
+        ferr = finish(0, 1);
+    } else {
+        std::vector<std::thread> th;
+        std::vector<cudaError_t> errs(n_thr, cudaSuccess);
+        for (size_t t = 1; t < n_thr; ++t) th.emplace_back([&, t] { errs[t] = finish(t, n_thr); });
+        errs[0] = finish(0, n_thr);
+        for (auto &x : th) x.join();
+        for (auto e : errs) if (e != cudaSuccess) ferr = e;
+    }
+    if (ferr != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "cudaEventSynchronize(chunk)", ferr);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream2));
     return LORAB200_OK;
 }
 
