@@ -18,21 +18,79 @@
 #include <cstdint>
 #include <cstring>
 #include <complex>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
+#ifdef REF_WITH_DEMOD
+/* LoRaDemod.cpp includes LoRaDetector.hpp itself (the header has no include guard) */
+#define private public
+#include "LoRaDemod.cpp"      /* from /root/reference via -I, unmodified */
+#undef private
+#else
 #include "LoRaDetector.hpp"   /* from /root/reference via -I */
+#endif
 #include "ChirpGenerator.hpp" /* from /root/reference via -I */
 
 #include "lora_oracle.h"      /* lo_cf / lo_result layouts */
 
-#ifdef REF_WITH_DEMOD
-#define private public
-#include "LoRaDemod.cpp"      /* from /root/reference via -I, unmodified */
-#undef private
-#endif
-
 typedef std::complex<float> cf;
+
+namespace {
+// Persistent worker pool so the timed CPU baseline does not pay thread creation on
+// every call (the reference itself is one thread per block; this is the fairest
+// "all host cores" arrangement of its own per-window loop).
+class Pool {
+public:
+    explicit Pool(int n) : n_(n), gen_(0), pending_(0), stop_(false)
+    {
+        for (int t = 0; t < n; ++t) th_.emplace_back([this, t] { run(t); });
+    }
+    ~Pool()
+    {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int size() const { return n_; }
+    void parallel(const std::function<void(int)> &fn)
+    {
+        std::unique_lock<std::mutex> l(m_);
+        fn_ = &fn; pending_ = n_; ++gen_;
+        cv_.notify_all();
+        done_.wait(l, [this] { return pending_ == 0; });
+    }
+private:
+    void run(int t)
+    {
+        unsigned long seen = 0;
+        for (;;) {
+            const std::function<void(int)> *fn;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            (*fn)(t);
+            { std::lock_guard<std::mutex> l(m_); if (--pending_ == 0) done_.notify_all(); }
+        }
+    }
+    int n_; unsigned long gen_; int pending_; bool stop_;
+    const std::function<void(int)> *fn_ = nullptr;
+    std::mutex m_; std::condition_variable cv_, done_;
+    std::vector<std::thread> th_;
+};
+Pool *get_pool(int n)
+{
+    static Pool *pool = nullptr;
+    if (!pool || pool->size() != n) { delete pool; pool = new Pool(n); }
+    return pool;
+}
+} // namespace
 
 extern "C" {
 
@@ -129,10 +187,10 @@ void ref_demod_windows(int sf, const lo_cf *iq_, size_t n_windows, size_t stride
         }
     };
     if (nthreads == 1 || n_windows < 2) { worker(0, n_windows); return; }
-    std::vector<std::thread> th;
-    for (int t = 0; t < nthreads; ++t)
-        th.emplace_back(worker, n_windows * size_t(t) / nthreads, n_windows * size_t(t + 1) / nthreads);
-    for (auto &t : th) t.join();
+    Pool *pool = get_pool(nthreads);
+    pool->parallel([&](int t) {
+        worker(n_windows * size_t(t) / nthreads, n_windows * size_t(t + 1) / nthreads);
+    });
 }
 
 #ifdef REF_WITH_DEMOD
