@@ -1,0 +1,199 @@
+/*
+ * loopback_driver.cpp -- TEST INFRASTRUCTURE ONLY (oracle/_ref/libloraloop.so).
+ *
+ * Runs the reference's full chain, restating TestLoopback.cpp:66-133 without the
+ * Pothos runtime:
+ *
+ *   packets -> /lora/lora_encoder -> /lora/lora_mod -> (+ AWGN) -> DEMOD -> /lora/lora_decoder
+ *
+ * where encoder, modulator and decoder are the UNMODIFIED reference blocks
+ * (/root/reference/LoRaEncoder.cpp, LoRaMod.cpp, LoRaDecoder.cpp compiled in place
+ * against our ministream Pothos surface) and DEMOD is either the unmodified reference
+ * LoRaDemod.cpp ("/lora/lora_demod") or our drop-in block shell
+ * (lora-sdr_b200/host/blocks/LoRaDemodB200.cpp, registered here as
+ * "/lora/lora_demod_b200").  Same bytes in, so the two demods can be compared
+ * symbol for symbol and label for label.
+ *
+ * The reference's own test takes its noise from PothosComms' /comms/noise_source
+ * (distribution unpinned, outside the tree); here it is i.i.d. N(0, sigma^2) per
+ * component from std::mt19937_64 with a recorded seed.
+ */
+#include <Pothos/Framework.hpp>
+
+#include <algorithm>
+#include <complex>
+#include <cstdint>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+namespace {
+
+typedef std::complex<float> cf;
+
+// adds seeded complex Gaussian noise to a stream (stand-in for /comms/noise_source + /comms/arithmetic ADD)
+class NoiseAdder : public Pothos::Block
+{
+public:
+    NoiseAdder(float sigma, uint64_t seed) : _sigma(sigma), _rng(seed), _dist(0.0f, 1.0f)
+    {
+        this->setupInput(0, typeid(cf));
+        this->setupOutput(0, typeid(cf));
+    }
+    void work(void)
+    {
+        auto in = this->input(0);
+        auto out = this->output(0);
+        const size_t n = std::min(in->elements(), out->elements());
+        if (n == 0) return;
+        const cf *src = in->buffer().as<const cf *>();
+        cf *dst = out->buffer().as<cf *>();
+        for (size_t i = 0; i < n; i++)
+        {
+            if (_sigma > 0) dst[i] = src[i] + cf(_sigma * _dist(_rng), _sigma * _dist(_rng));
+            else dst[i] = src[i];
+        }
+        in->consume(n);
+        out->produce(n);
+    }
+private:
+    float _sigma;
+    std::mt19937_64 _rng;
+    std::normal_distribution<float> _dist;
+};
+
+} // namespace
+
+extern "C" {
+
+struct LoopCfg
+{
+    int sf;
+    int cr;            /* 0..4 = "4/4".."4/8" */
+    int use_b200;      /* 0: reference LoRaDemod.cpp, 1: our block shell */
+    int debug_ports;   /* b200 only: produce raw/dec/fft dumps */
+    int padding;       /* mod.setPadding */
+    int mtu;           /* demod.setMTU */
+    int sync;          /* sync word */
+    float ampl;        /* mod.setAmplitude */
+    float sigma;       /* noise std-dev per component */
+    float thresh;      /* demod.setThreshold */
+    unsigned long long seed;
+};
+
+struct LoopOut
+{
+    int n_packets;                 /* decoded packets */
+    int lengths[64];
+    unsigned char bytes[64 * 256];
+    int n_sym_packets;             /* demod output packets */
+    int sym_lengths[64];
+    short symbols[64 * 1024];
+    unsigned long long dropped;
+    unsigned long long launches;   /* kernels launched by our demod */
+    unsigned long long samples;    /* samples through the demod */
+    int n_labels;                  /* labels on the demod's raw port */
+    char labels[256][24];
+    unsigned long long label_index[256];
+    int n_signals;                 /* error / power / snr emissions */
+    float signal_power[64];
+    int signal_error[64];
+    char error[256];
+};
+
+int loopback_run(const LoopCfg *cfg, const unsigned char *payloads, const int *lengths, int n_packets, LoopOut *out)
+{
+    std::memset(out, 0, sizeof(*out));
+    try
+    {
+        static const char *crs[] = {"4/4", "4/5", "4/6", "4/7", "4/8"};
+        std::unique_ptr<Pothos::Block> encoder(Pothos::BlockRegistry::make("/lora/lora_encoder"));
+        std::unique_ptr<Pothos::Block> mod(Pothos::BlockRegistry::make("/lora/lora_mod", size_t(cfg->sf)));
+        std::unique_ptr<Pothos::Block> demod(Pothos::BlockRegistry::make(
+            cfg->use_b200 ? "/lora/lora_demod_b200" : "/lora/lora_demod", size_t(cfg->sf)));
+        std::unique_ptr<Pothos::Block> decoder(Pothos::BlockRegistry::make("/lora/lora_decoder"));
+        NoiseAdder noise(cfg->sigma, cfg->seed);
+
+        encoder->call("setSpreadFactor", size_t(cfg->sf));
+        decoder->call("setSpreadFactor", size_t(cfg->sf));
+        encoder->call("setCodingRate", std::string(crs[cfg->cr]));
+        decoder->call("setCodingRate", std::string(crs[cfg->cr]));
+        mod->call("setAmplitude", cfg->ampl);
+        mod->call("setPadding", size_t(cfg->padding));
+        mod->call("setSync", (unsigned char)(cfg->sync));
+        demod->call("setSync", (unsigned char)(cfg->sync));
+        demod->call("setMTU", size_t(cfg->mtu));
+        demod->call("setThreshold", double(cfg->thresh));
+        if (cfg->use_b200) demod->call("setDebugPorts", bool(cfg->debug_ports != 0));
+
+        ministream::Topology topology;
+        topology.connect(encoder.get(), "0", mod.get(), "0");
+        topology.connect(mod.get(), "0", &noise, "0");
+        topology.connect(&noise, "0", demod.get(), "0");
+        topology.connect(demod.get(), "0", decoder.get(), "0");
+        demod->output("0")->collect = true;       /* also keep the symbol packets for comparison */
+        demod->output("raw")->collect = false;
+        topology.commit();
+
+        size_t ofs = 0;
+        for (int p = 0; p < n_packets; p++)
+        {
+            Pothos::Packet pkt;
+            pkt.payload = Pothos::BufferChunk(typeid(uint8_t), size_t(lengths[p]));
+            std::memcpy(pkt.payload.as<void *>(), payloads + ofs, size_t(lengths[p]));
+            ofs += size_t(lengths[p]);
+            ministream::Topology::feedMessage(encoder.get(), "0", Pothos::Object(pkt));
+        }
+        topology.run();
+
+        /* decoded packets */
+        size_t bo = 0;
+        for (auto &m : decoder->output("0")->collectedMessages)
+        {
+            if (out->n_packets >= 64) break;
+            const auto &pkt = m.extract<Pothos::Packet>();
+            if (bo + pkt.payload.length > sizeof(out->bytes)) break;
+            out->lengths[out->n_packets++] = int(pkt.payload.length);
+            std::memcpy(out->bytes + bo, pkt.payload.as<const void *>(), pkt.payload.length);
+            bo += pkt.payload.length;
+        }
+        /* demod symbol packets */
+        size_t so = 0;
+        for (auto &m : demod->output("0")->collectedMessages)
+        {
+            if (out->n_sym_packets >= 64) break;
+            const auto &pkt = m.extract<Pothos::Packet>();
+            const size_t ns = pkt.payload.length / 2;
+            if (so + ns > sizeof(out->symbols) / 2) break;
+            out->sym_lengths[out->n_sym_packets++] = int(ns);
+            std::memcpy(out->symbols + so, pkt.payload.as<const void *>(), ns * 2);
+            so += ns;
+        }
+        out->dropped = decoder->call<unsigned long long>("getDropped");
+        if (cfg->use_b200) out->launches = demod->call<unsigned long long>("getKernelLaunches");
+        out->samples = demod->input("0")->totalElements();
+        for (auto &l : demod->output("raw")->collectedLabels)
+        {
+            if (out->n_labels >= 256) break;
+            std::strncpy(out->labels[out->n_labels], l.id.c_str(), 23);
+            out->label_index[out->n_labels] = l.index;
+            out->n_labels++;
+        }
+        for (auto &s : demod->signalLog)
+        {
+            if (s.first == "power" && out->n_signals < 64) out->signal_power[out->n_signals++] = s.second[0].convert<float>();
+        }
+        int ne = 0;
+        for (auto &s : demod->signalLog)
+            if (s.first == "error" && ne < 64) out->signal_error[ne++] = s.second[0].convert<int>();
+        return 0;
+    }
+    catch (const std::exception &ex)
+    {
+        std::strncpy(out->error, ex.what(), sizeof(out->error) - 1);
+        return -1;
+    }
+}
+
+} /* extern "C" */

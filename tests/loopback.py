@@ -1,0 +1,56 @@
+"""ctypes access to oracle/_ref/libloraloop.so (the reference chain + our demod block shell)."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB = ROOT / "oracle" / "_ref" / "libloraloop.so"
+
+
+class LoopCfg(C.Structure):
+    _fields_ = [("sf", C.c_int), ("cr", C.c_int), ("use_b200", C.c_int), ("debug_ports", C.c_int),
+                ("padding", C.c_int), ("mtu", C.c_int), ("sync", C.c_int), ("ampl", C.c_float),
+                ("sigma", C.c_float), ("thresh", C.c_float), ("seed", C.c_ulonglong)]
+
+
+class LoopOut(C.Structure):
+    _fields_ = [("n_packets", C.c_int), ("lengths", C.c_int * 64), ("bytes", C.c_ubyte * (64 * 256)),
+                ("n_sym_packets", C.c_int), ("sym_lengths", C.c_int * 64), ("symbols", C.c_short * (64 * 1024)),
+                ("dropped", C.c_ulonglong), ("launches", C.c_ulonglong), ("samples", C.c_ulonglong),
+                ("n_labels", C.c_int), ("labels", (C.c_char * 24) * 256), ("label_index", C.c_ulonglong * 256),
+                ("n_signals", C.c_int), ("signal_power", C.c_float * 64), ("signal_error", C.c_int * 64),
+                ("error", C.c_char * 256)]
+
+
+def available():
+    return LIB.exists()
+
+
+def run(sf, cr, packets, use_b200=False, debug_ports=True, padding=512, mtu=512, sync=0x12, ampl=1.0,
+        sigma=0.0, thresh=-30.0, seed=1):
+    """packets: list of bytes objects.  Returns a dict with decoded packets, demod symbol packets, labels..."""
+    L = C.CDLL(str(LIB))
+    L.loopback_run.argtypes = [C.POINTER(LoopCfg), C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(LoopOut)]
+    cfg = LoopCfg(sf, cr, int(use_b200), int(debug_ports), padding, mtu, sync, ampl, sigma, thresh, seed)
+    blob = b"".join(packets)
+    lens = (C.c_int * len(packets))(*[len(p) for p in packets])
+    out = LoopOut()
+    rc = L.loopback_run(C.byref(cfg), blob, lens, len(packets), C.byref(out))
+    if rc != 0:
+        raise RuntimeError(out.error.decode())
+    dec, o = [], 0
+    raw = bytes(out.bytes)
+    for i in range(out.n_packets):
+        dec.append(raw[o:o + out.lengths[i]])
+        o += out.lengths[i]
+    syms, o = [], 0
+    sarr = np.ctypeslib.as_array(out.symbols)
+    for i in range(out.n_sym_packets):
+        syms.append(sarr[o:o + out.sym_lengths[i]].copy())
+        o += out.sym_lengths[i]
+    labels = [(out.labels[i].value.decode(), int(out.label_index[i])) for i in range(out.n_labels)]
+    return dict(decoded=dec, symbols=syms, dropped=int(out.dropped), launches=int(out.launches),
+                samples=int(out.samples), labels=labels,
+                power=[float(out.signal_power[i]) for i in range(out.n_signals)],
+                error=[int(out.signal_error[i]) for i in range(out.n_signals)])
