@@ -4,7 +4,12 @@
  * Runs the reference's full chain, restating TestLoopback.cpp:66-133 without the
  * Pothos runtime:
  *
- *   packets -> /lora/lora_encoder -> /lora/lora_mod -> (+ AWGN) -> DEMOD -> /lora/lora_decoder
+ *   packets -> /lora/lora_encoder -> /lora/lora_mod -> (+ AWGN) -> IQ      (loopback_tx)
+ *   IQ -> DEMOD -> /lora/lora_decoder -> packets                           (loopback_rx)
+ *
+ * (two halves so that both demods see the SAME samples: the reference encoder leaves the
+ * padding nibbles of the last interleaver block uninitialised, so two transmit runs of
+ * the same packets differ in their last few symbols)
  *
  * where encoder, modulator and decoder are the UNMODIFIED reference blocks
  * (/root/reference/LoRaEncoder.cpp, LoRaMod.cpp, LoRaDecoder.cpp compiled in place
@@ -18,7 +23,21 @@
  * (distribution unpinned, outside the tree); here it is i.i.d. N(0, sigma^2) per
  * component from std::mt19937_64 with a recorded seed.
  */
+ /* The reference demod reads _finefreqError (and _prevValue) before ever writing them
+ * (LoRaDemod.cpp:160,183 vs :386-392): with recycled heap memory that is a garbage fine
+ * tune walk or an out-of-range table index.  The reference source is compiled here
+ * unmodified, with its private members reachable so the harness can start it from the
+ * zero state our block shell documents. */
 #include <Pothos/Framework.hpp>
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <iostream>
+#include <sstream>
+#include <vector>
+#define private public        /* after the standard headers: only the reference class is affected */
+#include "LoRaDemod.cpp"      /* from /root/reference via -I, unmodified */
+#undef private
 
 #include <algorithm>
 #include <complex>
@@ -63,6 +82,17 @@ private:
     std::normal_distribution<float> _dist;
 };
 
+Pothos::Block *makeReferenceDemodFromZeroState(const size_t sf)
+{
+    LoRaDemod *d = new LoRaDemod(sf);
+    d->_finefreqError = 0;
+    d->_prevValue = 0;
+    d->_freqError = 0;
+    d->_symCount = 0;
+    return d;
+}
+Pothos::BlockRegistry registerReferenceDemodZero("/lora/lora_demod_ref0", &makeReferenceDemodFromZeroState);
+
 } // namespace
 
 extern "C" {
@@ -102,40 +132,26 @@ struct LoopOut
     char error[256];
 };
 
-int loopback_run(const LoopCfg *cfg, const unsigned char *payloads, const int *lengths, int n_packets, LoopOut *out)
+/* Transmit side: packets -> encoder -> mod -> (+ noise) -> IQ samples (complex64) into iq_out. */
+int loopback_tx(const LoopCfg *cfg, const unsigned char *payloads, const int *lengths, int n_packets,
+                float *iq_out, unsigned long long max_samples, unsigned long long *n_samples, char *err256)
 {
-    std::memset(out, 0, sizeof(*out));
     try
     {
         static const char *crs[] = {"4/4", "4/5", "4/6", "4/7", "4/8"};
         std::unique_ptr<Pothos::Block> encoder(Pothos::BlockRegistry::make("/lora/lora_encoder"));
         std::unique_ptr<Pothos::Block> mod(Pothos::BlockRegistry::make("/lora/lora_mod", size_t(cfg->sf)));
-        std::unique_ptr<Pothos::Block> demod(Pothos::BlockRegistry::make(
-            cfg->use_b200 ? "/lora/lora_demod_b200" : "/lora/lora_demod", size_t(cfg->sf)));
-        std::unique_ptr<Pothos::Block> decoder(Pothos::BlockRegistry::make("/lora/lora_decoder"));
         NoiseAdder noise(cfg->sigma, cfg->seed);
-
         encoder->call("setSpreadFactor", size_t(cfg->sf));
-        decoder->call("setSpreadFactor", size_t(cfg->sf));
         encoder->call("setCodingRate", std::string(crs[cfg->cr]));
-        decoder->call("setCodingRate", std::string(crs[cfg->cr]));
         mod->call("setAmplitude", cfg->ampl);
         mod->call("setPadding", size_t(cfg->padding));
         mod->call("setSync", (unsigned char)(cfg->sync));
-        demod->call("setSync", (unsigned char)(cfg->sync));
-        demod->call("setMTU", size_t(cfg->mtu));
-        demod->call("setThreshold", double(cfg->thresh));
-        if (cfg->use_b200) demod->call("setDebugPorts", bool(cfg->debug_ports != 0));
-
         ministream::Topology topology;
         topology.connect(encoder.get(), "0", mod.get(), "0");
         topology.connect(mod.get(), "0", &noise, "0");
-        topology.connect(&noise, "0", demod.get(), "0");
-        topology.connect(demod.get(), "0", decoder.get(), "0");
-        demod->output("0")->collect = true;       /* also keep the symbol packets for comparison */
-        demod->output("raw")->collect = false;
+        noise.output("0")->collect = true;
         topology.commit();
-
         size_t ofs = 0;
         for (int p = 0; p < n_packets; p++)
         {
@@ -146,6 +162,50 @@ int loopback_run(const LoopCfg *cfg, const unsigned char *payloads, const int *l
             ministream::Topology::feedMessage(encoder.get(), "0", Pothos::Object(pkt));
         }
         topology.run();
+        const auto &bytes = noise.output("0")->collectedBytes;
+        const unsigned long long n = bytes.size() / sizeof(cf);
+        if (n > max_samples) throw Pothos::Exception("loopback_tx", "iq_out too small");
+        std::memcpy(iq_out, bytes.data(), bytes.size());
+        *n_samples = n;
+        return 0;
+    }
+    catch (const std::exception &ex)
+    {
+        std::strncpy(err256, ex.what(), 255);
+        return -1;
+    }
+}
+
+/* Receive side: the SAME IQ samples -> DEMOD (reference or ours) -> decoder.
+ * `feed` samples are appended to the demod's input per scheduler pass (0 = all at once). */
+int loopback_rx(const LoopCfg *cfg, const float *iq, unsigned long long n_samples, unsigned long long feed, LoopOut *out)
+{
+    std::memset(out, 0, sizeof(*out));
+    try
+    {
+        static const char *crs[] = {"4/4", "4/5", "4/6", "4/7", "4/8"};
+        std::unique_ptr<Pothos::Block> demod(Pothos::BlockRegistry::make(
+            cfg->use_b200 ? "/lora/lora_demod_b200" : "/lora/lora_demod_ref0", size_t(cfg->sf)));
+        std::unique_ptr<Pothos::Block> decoder(Pothos::BlockRegistry::make("/lora/lora_decoder"));
+        decoder->call("setSpreadFactor", size_t(cfg->sf));
+        decoder->call("setCodingRate", std::string(crs[cfg->cr]));
+        demod->call("setSync", (unsigned char)(cfg->sync));
+        demod->call("setMTU", size_t(cfg->mtu));
+        demod->call("setThreshold", double(cfg->thresh));
+        if (cfg->use_b200) demod->call("setDebugPorts", bool(cfg->debug_ports != 0));
+
+        ministream::Topology topology;
+        topology.connect(demod.get(), "0", decoder.get(), "0");
+        demod->output("0")->collect = true;       /* also keep the symbol packets for comparison */
+        topology.commit();
+        const cf *src = reinterpret_cast<const cf *>(iq);
+        if (feed == 0) feed = n_samples;
+        for (unsigned long long at = 0; at < n_samples; at += feed)
+        {
+            const unsigned long long n = std::min(feed, n_samples - at);
+            ministream::Topology::feedStream(demod.get(), "0", src + at, n * sizeof(cf));
+            topology.run();
+        }
 
         /* decoded packets */
         size_t bo = 0;

@@ -27,16 +27,38 @@ def available():
     return LIB.exists()
 
 
-def run(sf, cr, packets, use_b200=False, debug_ports=True, padding=512, mtu=512, sync=0x12, ampl=1.0,
-        sigma=0.0, thresh=-30.0, seed=1):
-    """packets: list of bytes objects.  Returns a dict with decoded packets, demod symbol packets, labels..."""
+def _lib():
     L = C.CDLL(str(LIB))
-    L.loopback_run.argtypes = [C.POINTER(LoopCfg), C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(LoopOut)]
-    cfg = LoopCfg(sf, cr, int(use_b200), int(debug_ports), padding, mtu, sync, ampl, sigma, thresh, seed)
+    L.loopback_tx.argtypes = [C.POINTER(LoopCfg), C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_void_p,
+                              C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_char_p]
+    L.loopback_rx.argtypes = [C.POINTER(LoopCfg), C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.POINTER(LoopOut)]
+    return L
+
+
+def transmit(sf, cr, packets, padding=512, sync=0x12, ampl=1.0, sigma=0.0, seed=1):
+    """packets -> reference encoder -> reference modulator -> + N(0, sigma^2) noise.  Returns complex64 samples."""
+    L = _lib()
+    cfg = LoopCfg(sf, cr, 0, 0, padding, 0, sync, ampl, sigma, 0.0, seed)
     blob = b"".join(packets)
     lens = (C.c_int * len(packets))(*[len(p) for p in packets])
+    n_sym_max = sum(8 + 2 * (len(p) + 4) * 8 // max(1, sf - 2) + 16 for p in packets)
+    cap = (n_sym_max + len(packets) * (padding + 16)) * (1 << sf)
+    iq = np.empty(cap, np.complex64)
+    n = C.c_ulonglong()
+    err = C.create_string_buffer(256)
+    rc = L.loopback_tx(C.byref(cfg), blob, lens, len(packets), iq.ctypes.data_as(C.c_void_p), cap, C.byref(n), err)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return iq[: n.value].copy()
+
+
+def receive(sf, cr, iq, use_b200=False, debug_ports=True, mtu=512, sync=0x12, thresh=-30.0, feed=0):
+    """IQ -> demod (reference LoRaDemod.cpp or our block shell) -> reference decoder."""
+    L = _lib()
+    cfg = LoopCfg(sf, cr, int(use_b200), int(debug_ports), 0, mtu, sync, 1.0, 0.0, thresh, 0)
+    iq = np.ascontiguousarray(iq, np.complex64)
     out = LoopOut()
-    rc = L.loopback_run(C.byref(cfg), blob, lens, len(packets), C.byref(out))
+    rc = L.loopback_rx(C.byref(cfg), iq.ctypes.data_as(C.c_void_p), iq.size, feed, C.byref(out))
     if rc != 0:
         raise RuntimeError(out.error.decode())
     dec, o = [], 0
@@ -54,3 +76,9 @@ def run(sf, cr, packets, use_b200=False, debug_ports=True, padding=512, mtu=512,
                 samples=int(out.samples), labels=labels,
                 power=[float(out.signal_power[i]) for i in range(out.n_signals)],
                 error=[int(out.signal_error[i]) for i in range(out.n_signals)])
+
+
+def run(sf, cr, packets, use_b200=False, debug_ports=True, padding=512, mtu=512, sync=0x12, ampl=1.0,
+        sigma=0.0, thresh=-30.0, seed=1, feed=0):
+    iq = transmit(sf, cr, packets, padding=padding, sync=sync, ampl=ampl, sigma=sigma, seed=seed)
+    return receive(sf, cr, iq, use_b200=use_b200, debug_ports=debug_ports, mtu=mtu, sync=sync, thresh=thresh, feed=feed)

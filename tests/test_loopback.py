@@ -38,22 +38,33 @@ def test_reference_chain_with_noise(sf, cr, sigma):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("feed_windows", [0, 3, 37])
 @pytest.mark.parametrize("debug_ports", [True, False])
 @pytest.mark.parametrize("sf,cr,sigma", [(7, 1, 0.0), (7, 4, 0.5), (10, 3, 4.0), (10, 4, 4.0), (12, 4, 8.0)])
-def test_b200_demod_is_a_drop_in(cuda_ok, sf, cr, sigma, debug_ports):
+def test_b200_demod_is_a_drop_in(cuda_ok, sf, cr, sigma, debug_ports, feed_windows):
+    if sf == 12 and feed_windows == 3:
+        pytest.skip("slow")
     pk = _packets(1000 + sf * 10 + cr, n=2 if sf == 12 else 4, hi=48 if sf == 12 else 96)
-    ref = loopback.run(sf, cr, pk, use_b200=False, sigma=sigma, seed=7)
-    got = loopback.run(sf, cr, pk, use_b200=True, debug_ports=debug_ports, sigma=sigma, seed=7)
-    assert got["decoded"] == ref["decoded"] == pk
+    iq = loopback.transmit(sf, cr, pk, sigma=sigma, seed=7)            # the same samples for both demods
+    feed = feed_windows * (1 << sf) + (5 if feed_windows else 0)        # stream in ragged pieces
+    ref = loopback.receive(sf, cr, iq, use_b200=False, feed=feed)
+    got = loopback.receive(sf, cr, iq, use_b200=True, debug_ports=debug_ports, feed=feed)
+    # the reference demod may itself lose a packet under noise; what matters is that ours does the same
+    assert len(ref["decoded"]) >= len(pk) - 1 and all(d in pk for d in ref["decoded"]), "harness: reference chain failed"
+    if sigma == 0.0:
+        assert ref["decoded"] == pk
+    assert got["decoded"] == ref["decoded"]
     assert got["dropped"] == ref["dropped"]
     assert got["samples"] == ref["samples"], "consumed a different number of samples"
     assert len(got["symbols"]) == len(ref["symbols"])
     for a, b in zip(got["symbols"], ref["symbols"]):
         assert np.array_equal(a, b), "demodulated symbols differ from the reference demod"
     assert got["error"] == ref["error"]
-    assert np.allclose(got["power"], ref["power"], rtol=0, atol=0), "power signal not bit-identical"
+    assert got["power"] == ref["power"], "power signal not bit-identical"
     if debug_ports:
         assert got["labels"] == ref["labels"], "sync labels differ"
-    # the GPU did the work, in far fewer calls than windows
+    # the GPU did the work, in fewer calls than windows when whole buffers are available
     n = 1 << sf
-    assert 0 < got["launches"] < got["samples"] // n
+    assert got["launches"] > 0
+    if feed_windows == 0:
+        assert got["launches"] < got["samples"] // n
