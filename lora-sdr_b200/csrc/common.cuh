@@ -111,22 +111,20 @@ __device__ __forceinline__ float cx_abs(float2 a)
     return __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y))));
 }
 
-// LoRaDetector.hpp:50-61 on the device.  index and f_index are bit-exact;
-// power/power_avg use the device log10 (evaluated in double, rounded once),
-// glibc's log10f is not correctly rounded so those two may differ from the
-// reference by ~1 ulp of log10f (|delta| < 1e-5 dB).  lorab200_demod_host
-// finalises on the host instead and is bit-exact.
+// LoRaDetector.hpp:50-61 on the device.  index and f_index are bit-exact; power and
+// power_avg use the device log10f (<= 2 ulp) where the reference uses glibc's log10f
+// (not correctly rounded either), so they may differ from the reference by a few
+// 1e-6 dB (tests allow 1e-4 dB).  lorab200_demod_host finalises on the host instead
+// and is bit-exact.
 __device__ __forceinline__ void finalize_device(const RawResult &r, float power_scale,
                                                 lorab200_result *out)
 {
     const float noise = __fsqrt_rn(__double2float_rn(__dsub_rn(r.total, double(r.max_mag2))));
     const float fundamental = __fsqrt_rn(r.max_mag2);
-    const float lg_n = __double2float_rn(log10(double(noise)));
-    const float lg_f = __double2float_rn(log10(double(fundamental)));
     lorab200_result o;
     o.index = r.index;
-    o.power_avg = __fsub_rn(__fmul_rn(20.0f, lg_n), power_scale);
-    o.power = __fsub_rn(__fmul_rn(20.0f, lg_f), power_scale);
+    o.power_avg = __fsub_rn(__fmul_rn(20.0f, log10f(noise)), power_scale);
+    o.power = __fsub_rn(__fmul_rn(20.0f, log10f(fundamental)), power_scale);
     const float left = cx_abs(r.left), right = cx_abs(r.right);
     const double demon = __dsub_rn(__dsub_rn(__dmul_rn(2.0, double(fundamental)), double(right)), double(left));
     if (demon == 0.0) o.f_index = 0.0f;

@@ -69,7 +69,7 @@ struct FusedCfg {
     static constexpr int RAW_BYTES = RAWCAP * 32;
     static constexpr int RED_BYTES = GROUP > 32 ? 256 : 0; // cross-warp reduction scratch
     static constexpr int GROUP_BYTES = STAGES * STAGE_BYTES + X_BYTES + RAW_BYTES + RED_BYTES;
-    static constexpr int BAR_BYTES = 128 * ((GROUPS * STAGES * 8 + 127) / 128);
+    static constexpr int BAR_BYTES = 128 * (((GROUPS * STAGES + 1) * 8 + 127) / 128); // stage barriers + chirp barrier
     static constexpr int CHIRP_BYTES = CHIRP_SMEM ? N * 8 : 0;
     static constexpr int SMEM_BYTES = BAR_BYTES + CHIRP_BYTES + GROUPS * GROUP_BYTES;
     // two CTAs must fit in one SM: 228 KB per SM, 1 KB reserved per CTA
@@ -118,9 +118,15 @@ __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void fence_mbar_init()
+// programmatic dependent launch: let the next kernel in the stream start its prologue
+// while this grid drains / wait for the previous grid before touching its memory
+__device__ __forceinline__ void pdl_launch_dependents()
 {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_prior_grid()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 template <int GROUP>
 __device__ __forceinline__ void group_sync(int group_in_cta)
@@ -245,7 +251,6 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
     double *red_sum = reinterpret_cast<double *>(gptr + STAGES * C::STAGE_BYTES + C::X_BYTES + C::RAW_BYTES);
     float *red_val = reinterpret_cast<float *>(red_sum + 8);   // 8 doubles | 8 floats | 8 ints | 2 float2
     int *red_idx = reinterpret_cast<int *>(red_val + 8);
-    c64 *red_nb = reinterpret_cast<c64 *>(red_idx + 8);
 
     // ---- this group's contiguous range of tiles --------------------------------------------
     const uint32_t n_windows = uint32_t(p.n_windows);
@@ -257,12 +262,35 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
     const uint32_t my_tiles = per + (gid < rem ? 1u : 0u);
 
     // ---- one-time setup ---------------------------------------------------------------------
+    // Everything up to pdl_wait_prior_grid() only touches the tables (constant for the life
+    // of the context), so under programmatic dependent launch it overlaps the tail of the
+    // previous demod kernel in the stream.
+    pdl_launch_dependents();
+    const uint32_t cbar = smem_base + uint32_t(C::GROUPS * STAGES) * 8u; // chirp-table barrier (CTA wide)
     if (tg == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(bar0 + s * 8, 1);
-        fence_mbar_init();
+        if (tid == 0 && C::CHIRP_SMEM) mbar_init(cbar, 1);
+        fence_proxy_async(); // make the inits visible to the async (TMA) proxy
     }
-    group_sync<GROUP>(grp);
+    // twiddles of the radix-16 passes (registers for the whole persistent loop); issued
+    // first so their latency overlaps the barrier and the first TMA round trip
+    float2 tw1a[3], tw1b[4][3];
+    float2 tw2a[3], tw2b[4][3];
+    // pass-1 thread coordinates: lo = low B0 bits of the output index, hi = the rest
+    const int lo1 = t & (R0 - 1);
+    const int hi1 = t >> B0;
+    load_pass_tw<SF, B0>(p.tw, lo1, tw1a, tw1b);
+    if constexpr (C::NP == 3) load_pass_tw<SF, B0 + 4>(p.tw, t, tw2a, tw2b);
+
+    __syncthreads(); // barrier inits visible CTA-wide (the chirp barrier is shared by all groups)
+    if constexpr (C::CHIRP_SMEM) {
+        // chirp table -> shared memory by TMA (same linear layout as a window)
+        if (tid == 0) {
+            mbar_expect_tx(cbar, uint32_t(N) * 8u);
+            tma_load_1d(chirp_s, p.chirp, uint32_t(N) * 8u, cbar);
+        }
+    }
 
     auto issue = [&](uint32_t k, int s) {
         // TMA the whole tile k of this group (contiguous in HBM: stride == N)
@@ -274,27 +302,13 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
         mbar_expect_tx(bar0 + s * 8, bytes);
         tma_load_1d(gbase + s * C::STAGE_BYTES, p.iq + size_t(w0) * N, bytes, bar0 + s * 8);
     };
+    pdl_wait_prior_grid(); // from here on: the IQ batch and the result buffers
     if (tg == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s)
             if (uint32_t(s) < my_tiles) issue(s, s);
     }
-
-    // chirp table -> shared memory (same linear layout as a window)
-    if constexpr (C::CHIRP_SMEM) {
-        float2 *cs = reinterpret_cast<float2 *>(smem + C::BAR_BYTES);
-        for (int i = tid; i < N; i += C::CTA) cs[i] = p.chirp[i];
-        __syncthreads();
-    }
-
-    // twiddles of the radix-16 passes (registers for the whole persistent loop)
-    float2 tw1a[3], tw1b[4][3];
-    float2 tw2a[3], tw2b[4][3];
-    // pass-1 thread coordinates: lo = low B0 bits of the output index, hi = the rest
-    const int lo1 = t & (R0 - 1);
-    const int hi1 = t >> B0;
-    load_pass_tw<SF, B0>(p.tw, lo1, tw1a, tw1b);
-    if constexpr (C::NP == 3) load_pass_tw<SF, B0 + 4>(p.tw, t, tw2a, tw2b);
+    if constexpr (C::CHIRP_SMEM) mbar_wait(cbar, 0);
 
     // per-thread addresses (bytes)
     // pass-0 input: i(e, c) = ilow(e) + (N/R0)*c,  ilow = t (E==1) or ehi*2G + 2t + e0
@@ -317,15 +331,15 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
 
     auto flush = [&]() {
         // warp 0 of the group finalises the parked records, one per lane
+        group_sync<GROUP>(grp);
         if (tg < 32) {
-            __syncwarp();
             if (uint32_t(lane) < raw_cnt) {
                 const RawResult rr = rawbuf[lane];
                 if (p.raw) p.raw[raw_w0 + lane] = rr;
                 if (p.out) finalize_device(rr, p.power_scale, &p.out[raw_w0 + lane]);
             }
-            __syncwarp();
         }
+        group_sync<GROUP>(grp);
         raw_w0 += raw_cnt;
         raw_cnt = 0;
     };
@@ -507,22 +521,13 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             const int jl = bi > 0 ? bi - 1 : N - 1, jr = bi < N - 1 ? bi + 1 : 0;
             const int tl = jl & (G - 1), yl = jl / G, tr = jr & (G - 1), yr = jr / G;
             const c64 nbv = pick16(r, t == tl ? yl : yr);
-            c64 left, right;
-            if constexpr (G <= 32) {
-                const int base = lane - t; // first lane of this window
-                left = __shfl_sync(0xffffffffu, nbv, base + tl);
-                right = __shfl_sync(0xffffffffu, nbv, base + tr);
-            } else {
-                if (t == tl) red_nb[0] = nbv;
-                if (t == tr) red_nb[1] = nbv;
-                group_sync<GROUP>(grp);
-                left = red_nb[0]; right = red_nb[1];
-            }
-            if (t == 0 && live) {
-                RawResult rr;
-                rr.index = bi; rr.max_mag2 = bv; rr.total = sum;
-                rr.left = cunpack(left); rr.right = cunpack(right);
-                rawbuf[raw_cnt + wsub] = rr;
+            // the record of this window is assembled in shared memory by the three lanes that
+            // own its pieces; it is read back at the next flush (after a group-wide sync)
+            if (live) {
+                RawResult *slot = rawbuf + raw_cnt + wsub;
+                if (t == tl) slot->left = cunpack(nbv);
+                if (t == tr) slot->right = cunpack(nbv);
+                if (t == 0) { slot->index = bi; slot->max_mag2 = bv; slot->total = sum; }
             }
             {
                 uint32_t nw = n_windows - (tile0 + k) * WPT;
@@ -576,8 +581,20 @@ cudaError_t launch_fused_v(const DemodParams &p, const Pass0Tw &tw0, float2 phas
     unsigned long long ctas = (n_tiles + C::GROUPS - 1) / C::GROUPS;
     const unsigned long long cap = 2ull * (unsigned long long)sm_count; // persistent: 2 CTAs per SM
     if (ctas > cap) ctas = cap;
-    demod_fused_kernel<SF, DBG, FINE0><<<unsigned(ctas), C::CTA, C::SMEM_BYTES, s>>>(p, tw0, phasor);
-    return cudaGetLastError();
+    // Programmatic dependent launch: consecutive demod launches on a stream may overlap
+    // this kernel's prologue (barrier init, table loads) with the previous kernel's tail;
+    // the kernel itself waits (griddepcontrol.wait) before touching the batch or the results.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(ctas));
+    cfg.blockDim = dim3(C::CTA);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, demod_fused_kernel<SF, DBG, FINE0>, p, tw0, phasor);
 }
 
 template <int SF>
