@@ -236,7 +236,9 @@ def main():
     m.build()
     sf, nw, K, W = args.sf, args.windows, args.steps, args.warmup
     n = 1 << sf
-    d = m.Demod(sf, device=local, flags=m.FLAG_SIMPLE_ONLY if args.simple else m.FLAG_DEFAULT)
+    # the synthetic batches are resident and never rewritten: let consecutive launches overlap
+    # their first loads with the previous launch's tail (LORAB200_FLAG_INPUT_STABLE)
+    d = m.Demod(sf, device=local, flags=m.FLAG_SIMPLE_ONLY if args.simple else m.FLAG_INPUT_STABLE)
 
     # ---- tables: rank 0's copy is broadcast over NCCL (the only collective on this path) -------
     if world > 1:
@@ -359,7 +361,7 @@ def main():
         "config": {"workload": workload_name(sf, nw), "sf": sf, "windows_per_step_per_gpu": nw,
                    "l2": f"inputs rotate over {nbuf} distinct {step_bytes >> 20} MiB buffers "
                          f"({nbuf * step_bytes >> 20} MiB > 3x L2), so every step streams from HBM",
-                   "timing": "K steps captured in one CUDA graph, CUDA events on the launching stream",
+                   "timing": "K steps captured in one CUDA graph (programmatic dependent launch between steps, LORAB200_FLAG_INPUT_STABLE), CUDA events on the launching stream",
                    "parity_spot_check": parity, "sharding": "windows block-partitioned per rank, no data-path collective"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Msymbols/s", "h2d_bytes_per_step": step_bytes,

@@ -83,6 +83,11 @@ typedef struct {
 /* Flags for lorab200_create. */
 #define LORAB200_FLAG_DEFAULT      0u
 #define LORAB200_FLAG_SIMPLE_ONLY  1u  /* force the simple one-stage-per-sync kernel (debug / cross-check) */
+/* The IQ buffers given to lorab200_demod_dev are never written by the kernel launched
+ * immediately before on the same stream (e.g. a receiver that double-buffers its input):
+ * consecutive demod launches then overlap their first loads with the previous launch's
+ * tail (programmatic dependent launch).  Results are unaffected either way. */
+#define LORAB200_FLAG_INPUT_STABLE 2u
 
 /* ---- lifetime -------------------------------------------------------------- */
 

@@ -29,7 +29,7 @@ LIB_PATH = PKG_DIR / "liblorab200.so"
 STAMP_PATH = PKG_DIR / "liblorab200.so.stamp"
 
 TABLE_UP, TABLE_DOWN, TABLE_FINE, TABLE_TWIDDLE = 0, 1, 2, 3
-FLAG_DEFAULT, FLAG_SIMPLE_ONLY = 0, 1
+FLAG_DEFAULT, FLAG_SIMPLE_ONLY, FLAG_INPUT_STABLE = 0, 1, 2
 FINE_STEPS = 128
 
 RESULT_DTYPE = np.dtype(

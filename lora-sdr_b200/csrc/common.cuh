@@ -41,6 +41,7 @@ struct DemodParams {
     RawResult *raw;           // raw records, or nullptr
     float2 *fft;              // optional [W][N]
     float2 *dec;              // optional [W][N]
+    unsigned int early_iq;    // LORAB200_FLAG_INPUT_STABLE: IQ may be prefetched before the prior grid drains
 };
 
 // ---- exact complex arithmetic --------------------------------------------------

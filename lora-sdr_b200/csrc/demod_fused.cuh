@@ -54,9 +54,18 @@ struct FusedCfg {
     static constexpr int TILE = GROUP * 16;             // samples per tile
     static constexpr int CTA = 256;
     static constexpr int GROUPS = CTA / GROUP;          // groups per CTA
-    static constexpr int STAGES = 2;
+    // Occupancy plan: 2 CTAs per SM (<= 128 registers), two TMA stages per group.
+    // (Measured alternative for the two-pass SFs, -DLORAB200_TRY_3CTA: 3 CTAs per SM at
+    // 80 registers with one stage per group is slower -- SF7 3083 vs 3674 Msym/s.)
+#ifdef LORAB200_TRY_3CTA
+    static constexpr int CTAS_PER_SM = (NP == 2) ? 3 : 2;
+#else
+    static constexpr int CTAS_PER_SM = 2;
+#endif
+    static constexpr int STAGES = (CTAS_PER_SM == 3) ? 1 : 2;
     static constexpr bool CHIRP_SMEM = (SF <= 10);      // chirp table staged in shared memory
-    static constexpr int RAWCAP = 32;                   // raw results parked per group before a flush
+    // raw results parked per group before a flush (a multiple of WPT)
+    static constexpr int RAWCAP = (CTAS_PER_SM == 3) ? (SF == 7 ? 12 : 24) : 32;
 
     // exchange layout: natural output index j -> padded element offset inside the window
     __host__ __device__ static constexpr int pad(int j)
@@ -69,11 +78,12 @@ struct FusedCfg {
     static constexpr int RAW_BYTES = RAWCAP * 32;
     static constexpr int RED_BYTES = GROUP > 32 ? 256 : 0; // cross-warp reduction scratch
     static constexpr int GROUP_BYTES = STAGES * STAGE_BYTES + X_BYTES + RAW_BYTES + RED_BYTES;
-    static constexpr int BAR_BYTES = 128 * (((GROUPS * STAGES + 1) * 8 + 127) / 128); // stage barriers + chirp barrier
+    static constexpr int BAR_BYTES = 16 * (((GROUPS * STAGES + 1) * 8 + 15) / 16); // stage barriers + chirp barrier
     static constexpr int CHIRP_BYTES = CHIRP_SMEM ? N * 8 : 0;
     static constexpr int SMEM_BYTES = BAR_BYTES + CHIRP_BYTES + GROUPS * GROUP_BYTES;
-    // two CTAs must fit in one SM: 228 KB per SM, 1 KB reserved per CTA
-    static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "shared memory budget: 2 CTAs per SM");
+    // the planned number of CTAs must fit in one SM: 228 KB per SM, 1 KB reserved per CTA
+    static_assert(CTAS_PER_SM * (SMEM_BYTES + 1024) <= 233472, "shared memory budget");
+    static_assert(RAWCAP % WPT == 0 && RAWCAP <= 32, "RAWCAP");
 };
 
 // Uniform twiddles used inside pass 0 (kissfft.hh:141-143 with m = 2 or 4): passed by
@@ -143,11 +153,15 @@ __device__ __forceinline__ c64 lds64(uint32_t addr)
 }
 __device__ __forceinline__ void lds128(uint32_t addr, c64 &a, c64 &b)
 {
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+    float x, y, z, w;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(addr));
+    a = cpack(x, y);
+    b = cpack(z, w);
 }
 __device__ __forceinline__ void sts64(uint32_t addr, c64 v)
 {
-    asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+    const float2 f = cunpack(v);
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(f.x), "f"(f.y) : "memory");
 }
 
 // base-4 digit reversal of v over `bits` bits (bits even): kissfft's input permutation
@@ -174,19 +188,17 @@ __device__ __forceinline__ void radix16(c64 (&r)[16], const float2 (&twa)[3], co
 {
 #pragma unroll
     for (int qd = 0; qd < 4; ++qd) {
-        c64 a1 = pcx_mul(r[qd * 4 + 1], twa[0]);
-        c64 a2 = pcx_mul(r[qd * 4 + 2], twa[1]);
-        c64 a3 = pcx_mul(r[qd * 4 + 3], twa[2]);
-        p_bfly4(r[qd * 4 + 0], a1, a2, a3);
-        r[qd * 4 + 1] = a1; r[qd * 4 + 2] = a2; r[qd * 4 + 3] = a3;
+        r[qd * 4 + 1] = pcx_mul(r[qd * 4 + 1], twa[0]);
+        r[qd * 4 + 2] = pcx_mul(r[qd * 4 + 2], twa[1]);
+        r[qd * 4 + 3] = pcx_mul(r[qd * 4 + 3], twa[2]);
+        p_bfly4(r[qd * 4 + 0], r[qd * 4 + 1], r[qd * 4 + 2], r[qd * 4 + 3]);
     }
 #pragma unroll
     for (int qc = 0; qc < 4; ++qc) {
-        c64 a1 = pcx_mul(r[4 + qc], twb[qc][0]);
-        c64 a2 = pcx_mul(r[8 + qc], twb[qc][1]);
-        c64 a3 = pcx_mul(r[12 + qc], twb[qc][2]);
-        p_bfly4(r[qc], a1, a2, a3);
-        r[4 + qc] = a1; r[8 + qc] = a2; r[12 + qc] = a3;
+        r[4 + qc] = pcx_mul(r[4 + qc], twb[qc][0]);
+        r[8 + qc] = pcx_mul(r[8 + qc], twb[qc][1]);
+        r[12 + qc] = pcx_mul(r[12 + qc], twb[qc][2]);
+        p_bfly4(r[qc], r[4 + qc], r[8 + qc], r[12 + qc]);
     }
 }
 
@@ -225,7 +237,7 @@ __device__ __forceinline__ c64 pick16(const c64 (&r)[16], int slot)
 // FINE0: multiply every dechirped sample by one constant fine-tune phasor (the
 //        LoRaDemod.cpp:159 form when _finefreqError == 0: index constant over the batch)
 template <int SF, bool DBG, bool FINE0>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, FusedCfg<SF>::CTAS_PER_SM)
 demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_phasor)
 {
     using C = FusedCfg<SF>;
@@ -302,8 +314,17 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
         mbar_expect_tx(bar0 + s * 8, bytes);
         tma_load_1d(gbase + s * C::STAGE_BYTES, p.iq + size_t(w0) * N, bytes, bar0 + s * 8);
     };
-    pdl_wait_prior_grid(); // from here on: the IQ batch and the result buffers
-    if (tg == 0) {
+    // With LORAB200_FLAG_INPUT_STABLE the caller guarantees that the IQ batch was not
+    // produced by the kernel launched just before this one on the stream (a streaming
+    // receiver's double buffering), so the first TMA loads may start before the prior
+    // grid has drained; the results are still only written after the wait.
+    if (p.early_iq && tg == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            if (uint32_t(s) < my_tiles) issue(s, s);
+    }
+    pdl_wait_prior_grid(); // from here on: the IQ batch (unless stable) and the result buffers
+    if (!p.early_iq && tg == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s)
             if (uint32_t(s) < my_tiles) issue(s, s);
@@ -439,11 +460,10 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
 #pragma unroll
                     for (int a = 0; a < 4; ++a) p_bfly2(v[a], v[a + 4]);
                     p_bfly4(v[0], v[1], v[2], v[3]);                       // k = 0: tw[0]
-                    c64 a1 = pcx_mul(v[5], p0tw.w[0][0]);
-                    c64 a2 = pcx_mul(v[6], p0tw.w[1][0]);
-                    c64 a3 = pcx_mul(v[7], p0tw.w[2][0]);
-                    p_bfly4(v[4], a1, a2, a3);
-                    v[5] = a1; v[6] = a2; v[7] = a3;
+                    v[5] = pcx_mul(v[5], p0tw.w[0][0]);
+                    v[6] = pcx_mul(v[6], p0tw.w[1][0]);
+                    v[7] = pcx_mul(v[7], p0tw.w[2][0]);
+                    p_bfly4(v[4], v[5], v[6], v[7]);
                 } else {
                     // radix-4 (m=1) over qa for each qb (slots qb + 4*qa), then radix-4 (m=4)
 #pragma unroll
@@ -451,11 +471,10 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
                     p_bfly4(v[0], v[1], v[2], v[3]);                       // k = 0
 #pragma unroll
                     for (int kk = 1; kk < 4; ++kk) {
-                        c64 a1 = pcx_mul(v[4 * kk + 1], p0tw.w[0][kk - 1]);
-                        c64 a2 = pcx_mul(v[4 * kk + 2], p0tw.w[1][kk - 1]);
-                        c64 a3 = pcx_mul(v[4 * kk + 3], p0tw.w[2][kk - 1]);
-                        p_bfly4(v[4 * kk], a1, a2, a3);
-                        v[4 * kk + 1] = a1; v[4 * kk + 2] = a2; v[4 * kk + 3] = a3;
+                        v[4 * kk + 1] = pcx_mul(v[4 * kk + 1], p0tw.w[0][kk - 1]);
+                        v[4 * kk + 2] = pcx_mul(v[4 * kk + 2], p0tw.w[1][kk - 1]);
+                        v[4 * kk + 3] = pcx_mul(v[4 * kk + 3], p0tw.w[2][kk - 1]);
+                        p_bfly4(v[4 * kk], v[4 * kk + 1], v[4 * kk + 2], v[4 * kk + 3]);
                     }
                 }
             }
@@ -483,15 +502,44 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             }
 
             // ---- peak scan: thread holds bins j = t + G*y, y ascending (LoRaDetector.hpp:36-48) ----------
-            float bv = 0.0f; int by = 0;
-            double sum0 = 0.0, sum1 = 0.0;
+            // Tournament over the 16 bins instead of a 16-long compare chain: at every node the
+            // lower bin wins unless the higher one is strictly larger, which is exactly what the
+            // sequential strict-'>' scan yields; a final strict compare against 0 reproduces the
+            // "running maximum starts at 0" (an all-zero or all-NaN window keeps index 0).
+            float m2[16];
 #pragma unroll
-            for (int y = 0; y < 16; ++y) {
-                const float m2 = pcx_mag2(r[y]);
-                if (y & 1) sum1 += double(m2); else sum0 += double(m2);
-                if (m2 > bv) { bv = m2; by = y; }
+            for (int y = 0; y < 16; ++y) m2[y] = pcx_mag2(r[y]);
+            float bv; int by;
+            {
+                float v8[8]; int i8[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const bool hi = m2[2 * q + 1] > m2[2 * q];
+                    v8[q] = hi ? m2[2 * q + 1] : m2[2 * q];
+                    i8[q] = hi ? 2 * q + 1 : 2 * q;
+                }
+                float v4[4]; int i4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool hi = v8[2 * q + 1] > v8[2 * q];
+                    v4[q] = hi ? v8[2 * q + 1] : v8[2 * q];
+                    i4[q] = hi ? i8[2 * q + 1] : i8[2 * q];
+                }
+                const bool h0 = v4[1] > v4[0], h1 = v4[3] > v4[2];
+                const float va = h0 ? v4[1] : v4[0], vb = h1 ? v4[3] : v4[2];
+                const int ia = h0 ? i4[1] : i4[0], ib = h1 ? i4[3] : i4[2];
+                const bool hh = vb > va;
+                bv = hh ? vb : va;
+                by = hh ? ib : ia;
+                if (!(bv > 0.0f)) { bv = 0.0f; by = 0; }
             }
-            double sum = sum0 + sum1;
+            // double sum of the float |bin|^2 terms, four partial chains
+            double s0 = double(m2[0]), s1 = double(m2[1]), s2 = double(m2[2]), s3 = double(m2[3]);
+#pragma unroll
+            for (int y = 4; y < 16; y += 4) {
+                s0 += double(m2[y]); s1 += double(m2[y + 1]); s2 += double(m2[y + 2]); s3 += double(m2[y + 3]);
+            }
+            double sum = (s0 + s1) + (s2 + s3);
             int bi = t + G * by;
             if constexpr (DBG) {
                 if (p.fft && live) {
@@ -540,6 +588,7 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
 }
 
 // ---- host side -------------------------------------------------------------------------
+#ifndef LORAB200_KERNEL_ONLY // (tools: compile a single instantiation for SASS inspection)
 inline bool fused_applicable(int sf, const DemodParams &p)
 {
     if (sf < 7 || sf > 12) return false;
@@ -579,7 +628,7 @@ cudaError_t launch_fused_v(const DemodParams &p, const Pass0Tw &tw0, float2 phas
     }
     const unsigned long long n_tiles = (p.n_windows + C::WPT - 1) / C::WPT;
     unsigned long long ctas = (n_tiles + C::GROUPS - 1) / C::GROUPS;
-    const unsigned long long cap = 2ull * (unsigned long long)sm_count; // persistent: 2 CTAs per SM
+    const unsigned long long cap = (unsigned long long)C::CTAS_PER_SM * (unsigned long long)sm_count; // persistent
     if (ctas > cap) ctas = cap;
     // Programmatic dependent launch: consecutive demod launches on a stream may overlap
     // this kernel's prologue (barrier init, table loads) with the previous kernel's tail;
@@ -622,5 +671,6 @@ inline cudaError_t launch_fused(int sf, const DemodParams &p, const Pass0Tw &tw0
     default: return cudaErrorInvalidValue;
     }
 }
+#endif // LORAB200_KERNEL_ONLY
 
 } // namespace lorab200

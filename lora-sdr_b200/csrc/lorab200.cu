@@ -188,6 +188,7 @@ int run_demod(lorab200_ctx *c, const void *iq_dev, size_t n_windows, size_t stri
     p.fft = static_cast<float2 *>(fft_dev);
     p.dec = static_cast<float2 *>(dec_dev);
     p.fine_len = int(c->n * kFineSteps);
+    p.early_iq = (c->flags & LORAB200_FLAG_INPUT_STABLE) ? 1u : 0u;
 
     if (fine) {
         if (fine->index < 0 || fine->index >= p.fine_len)
