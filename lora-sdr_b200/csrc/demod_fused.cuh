@@ -62,8 +62,10 @@ struct FusedCfg {
 #else
     static constexpr int CTAS_PER_SM = 2;
 #endif
-    static constexpr int STAGES = (CTAS_PER_SM == 3) ? 1 : 2;
-    static constexpr bool CHIRP_SMEM = (SF <= 10);      // chirp table staged in shared memory
+    // SF >= 11: one stage (a window takes far longer to process than a tile takes to arrive,
+    // and the stage is handed back to the TMA right after it has been copied to registers)
+    static constexpr int STAGES = (CTAS_PER_SM == 3 || SF >= 11) ? 1 : 2;
+    static constexpr bool CHIRP_SMEM = true;            // chirp table staged in shared memory (TMA)
     // raw results parked per group before a flush (a multiple of WPT)
     static constexpr int RAWCAP = (CTAS_PER_SM == 3) ? (SF == 7 ? 12 : 24) : 32;
 
@@ -289,11 +291,18 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
     // first so their latency overlaps the barrier and the first TMA round trip
     float2 tw1a[3], tw1b[4][3];
     float2 tw2a[3], tw2b[4][3];
-    // pass-1 thread coordinates: lo = low B0 bits of the output index, hi = the rest
-    const int lo1 = t & (R0 - 1);
-    const int hi1 = t >> B0;
+    // Thread coordinates of the radix-16 passes.  Two passes: lo1 = t (hi1 = 0).  Three
+    // passes: thread t of the window plays (lo, hi) = (t >> 4, t & 15) in pass 1 -- output
+    // index lo | y << B0 | hi << (B0+4) -- and (lo, m = t & 15) in pass 2 -- output index
+    // tL | y << (B0+4) with tL = lo | m << B0.  The second exchange then only moves data
+    // between the 16 threads of one lo-group, which are 16 consecutive lanes of one warp:
+    // it needs a __syncwarp, not a group barrier, and each thread writes back exactly the
+    // 16 slots it gathered.
+    const int lo1 = (C::NP == 3) ? (t >> 4) : t;
+    const int hi1 = (C::NP == 3) ? (t & 15) : 0;
+    const int tL = (C::NP == 3) ? (lo1 | (hi1 << B0)) : t;   // owner coordinate of the final bins tL + G*y
     load_pass_tw<SF, B0>(p.tw, lo1, tw1a, tw1b);
-    if constexpr (C::NP == 3) load_pass_tw<SF, B0 + 4>(p.tw, t, tw2a, tw2b);
+    if constexpr (C::NP == 3) load_pass_tw<SF, B0 + 4>(p.tw, tL, tw2a, tw2b);
 
     __syncthreads(); // barrier inits visible CTA-wide (the chirp barrier is shared by all groups)
     if constexpr (C::CHIRP_SMEM) {
@@ -345,7 +354,7 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
     }
     // pass-1 gather/scatter: j = lo | y << B0 | hi << (B0+4);  pass-2 gather: j = t | y << (B0+4)
     const uint32_t ga1 = wx + uint32_t(C::pad(lo1 | (hi1 << (B0 + 4)))) * 8u;
-    const uint32_t ga2 = wx + uint32_t(C::pad(t)) * 8u;
+    const uint32_t ga2 = wx + uint32_t(C::pad(tL)) * 8u;
 
     uint32_t raw_cnt = 0;           // raw results parked in rawbuf
     uint32_t raw_w0 = tile0 * WPT;  // window index of rawbuf[0]
@@ -492,10 +501,12 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             // ---- pass 1 (and exchange 1 + pass 2) -----------------------------------------------------
             radix16(r, tw1a, tw1b);
             if constexpr (C::NP == 3) {
-                group_sync<GROUP>(grp);          // everyone has gathered exchange 0: reuse the buffer
+                // exchange 1, in place: every thread overwrites the 16 slots it has just gathered
+                // (no other thread reads them in exchange 0), and the gather below only touches
+                // slots written by the 16 lanes of this thread's lo-group
 #pragma unroll
                 for (int y = 0; y < 16; ++y) sts64(ga1 + uint32_t(C::pad(y << B0)) * 8u, r[y]);
-                group_sync<GROUP>(grp);
+                __syncwarp();
 #pragma unroll
                 for (int y = 0; y < 16; ++y) r[y] = lds64(ga2 + uint32_t(C::pad(y << (B0 + 4))) * 8u);
                 radix16(r, tw2a, tw2b);
@@ -540,11 +551,11 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
                 s0 += double(m2[y]); s1 += double(m2[y + 1]); s2 += double(m2[y + 2]); s3 += double(m2[y + 3]);
             }
             double sum = (s0 + s1) + (s2 + s3);
-            int bi = t + G * by;
+            int bi = tL + G * by;
             if constexpr (DBG) {
                 if (p.fft && live) {
 #pragma unroll
-                    for (int y = 0; y < 16; ++y) p.fft[size_t(w) * N + t + G * y] = cunpack(r[y]);
+                    for (int y = 0; y < 16; ++y) p.fft[size_t(w) * N + tL + G * y] = cunpack(r[y]);
                 }
             }
             // reduce over the window's G threads
@@ -568,13 +579,13 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             // neighbours of the peak, (bi-1) mod N and (bi+1) mod N, live in other threads' registers
             const int jl = bi > 0 ? bi - 1 : N - 1, jr = bi < N - 1 ? bi + 1 : 0;
             const int tl = jl & (G - 1), yl = jl / G, tr = jr & (G - 1), yr = jr / G;
-            const c64 nbv = pick16(r, t == tl ? yl : yr);
+            const c64 nbv = pick16(r, tL == tl ? yl : yr);
             // the record of this window is assembled in shared memory by the three lanes that
             // own its pieces; it is read back at the next flush (after a group-wide sync)
             if (live) {
                 RawResult *slot = rawbuf + raw_cnt + wsub;
-                if (t == tl) slot->left = cunpack(nbv);
-                if (t == tr) slot->right = cunpack(nbv);
+                if (tL == tl) slot->left = cunpack(nbv);
+                if (tL == tr) slot->right = cunpack(nbv);
                 if (t == 0) { slot->index = bi; slot->max_mag2 = bv; slot->total = sum; }
             }
             {

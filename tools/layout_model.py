@@ -57,13 +57,19 @@ def x_of_c(b0, cc):
     return ((cc & 3) << 2) | (cc >> 2)
 
 
+SF_NOW = 7
+
+
 def pad(j):
-    """exchange layout: one pad element per 16 (and per 256) keeps base+imm addressing"""
+    """exchange layout (FusedCfg::pad): pads keep every address = thread base + immediate.
+    SF7 (two windows per half-warp) needs its own pattern and a window stride of 152."""
+    if SF_NOW == 7:
+        return j + (j >> 3) + 2 * (j >> 5)
     return j + (j >> 4) + (j >> 8)
 
 
 def win_stride(c):
-    return pad(c["n"] - 1) + 1 + (1 if c["g"] < 16 else 0) * 8  # see check below
+    return 152 if c["sf"] == 7 else pad(c["n"] - 1) + 1
 
 
 def bfly4(a0, a1, a2, a3):
@@ -76,6 +82,8 @@ def bfly4(a0, a1, a2, a3):
 
 
 def model_window(sf, xin, chirp, tw, accesses):
+    global SF_NOW
+    SF_NOW = sf
     c = cfg(sf)
     n, b0, r0, E, g = c["n"], c["b0"], c["r0"], c["e"], c["g"]
     hi_bits = sf - b0
@@ -122,17 +130,25 @@ def model_window(sf, xin, chirp, tw, accesses):
                 exch[j] = v[(e, cc)]
                 accesses.setdefault(("x0write", e, cc), []).append((t, pad(j), 8))
     # ---- passes 1..
+    # Two-pass sizes: thread t has lo = t.  Three-pass sizes: physical thread tau plays
+    # (lo, hi) = (tau >> 4, tau & 15) in pass 1 and (lo, m) = (tau >> 4, tau & 15) in pass 2
+    # (logical pass-2 coordinate lo | m << b0), so that the second exchange only moves data
+    # between the 16 threads of one lo-group, i.e. inside a warp.
     a = b0
     F = exch
     for p in range(1, c["npass"]):
         out = {}
-        for t in range(g):
-            lo = t & ((1 << a) - 1)
-            hi = t >> a
+        for tau in range(g):
+            if c["npass"] == 2:
+                lo, hi = tau, 0
+            elif p == 1:
+                lo, hi = tau >> 4, tau & 15
+            else:
+                lo, hi = (tau >> 4) | ((tau & 15) << b0), 0
             r = []
             for y in range(16):
                 j = lo | (y << a) | (hi << (a + 4))
-                accesses.setdefault((f"x{p-1}read", y), []).append((t, pad(j), 8))
+                accesses.setdefault((f"x{p-1}read", y), []).append((tau, pad(j), 8))
                 r.append(F[j])
             m = 1 << a
             fsa = n // (4 * m)
@@ -153,24 +169,15 @@ def model_window(sf, xin, chirp, tw, accesses):
                 j = lo | (y << a) | (hi << (a + 4))
                 out[j] = r[y]
                 if p + 1 < c["npass"]:
-                    accesses.setdefault((f"x{p}write", y), []).append((t, pad(j), 8))
+                    accesses.setdefault((f"x{p}write", y), []).append((tau, pad(j), 8))
         F = out
         a += 4
     return np.array([F[j] for j in range(n)])
 
 
-def conflict_degree(acc, c):
-    """acc: list of (thread, element_index(8B units), bytes) for ONE instruction, all threads of a window."""
-    g, group, wpt = c["g"], c["group"], c["wpt"]
-    ws = win_stride(c) if True else c["n"]
-    worst = 1
-    lanes = {}
-    # expand to a full warp: windows of a tile sit at w*win_stride (exchange) -- for the
-    # p0 read the stage is linear: w*n
-    return lanes, worst
-
-
 def check_banks(sf, accesses):
+    global SF_NOW
+    SF_NOW = sf
     c = cfg(sf)
     g, wpt, n = c["g"], c["wpt"], c["n"]
     bad = []
