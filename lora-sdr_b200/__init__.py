@@ -107,9 +107,10 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise RuntimeError(f"{LIB_PATH} is not built; run __graft_entry__.build() (no CPU fallback exists)")
-    L = C.CDLL(str(LIB_PATH))
+    path = Path(os.environ.get("LORAB200_LIB", str(LIB_PATH)))   # LORAB200_LIB: kernel-tuning experiments
+    if not path.exists():
+        raise RuntimeError(f"{path} is not built; run __graft_entry__.build() (no CPU fallback exists)")
+    L = C.CDLL(str(path))
     vp, sz, i32p = C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)
     L.lorab200_abi_version.restype = C.c_int
     L.lorab200_strerror.restype = C.c_char_p

@@ -1,0 +1,140 @@
+#!/usr/bin/env python3
+"""Turn the ncu reports brought back in gpurun_out/ into the committed summaries under profiles/.
+
+    python tools/summarize_ncu.py r01          # reads gpurun_out/prof_sf{7,10,12}.ncu-rep, launches_sf7.csv
+
+Writes profiles/<round>_ncu_sf<SF>.json (key metrics + instruction mix + stall reasons),
+profiles/<round>_launches_sf7.csv (the launch list), and profiles/traffic.json (DRAM bytes
+per launch, read by bench.py for roofline.traffic).
+"""
+import collections
+import csv
+import io
+import json
+import re
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+OUT = ROOT / "profiles"
+SRC = ROOT / "gpurun_out"
+
+KEYS = [
+    "gpu__time_duration.sum", "sm__cycles_elapsed.avg", "smsp__cycles_active.avg",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__warps_active.avg.per_cycle_active", "launch__registers_per_thread", "launch__grid_size",
+    "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "lts__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+]
+UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
+
+
+def ncu(*args):
+    return subprocess.run(["ncu", *args], capture_output=True, text=True).stdout
+
+
+def raw_metrics(rep):
+    rows = list(csv.reader(io.StringIO(ncu("-i", str(rep), "--page", "raw", "--csv"))))
+    hdr, units, data = rows[0], rows[1], rows[2]
+    m = {}
+    for i, h in enumerate(hdr):
+        if h in KEYS or h == "Kernel Name":
+            v = data[i]
+            try:
+                v = float(v.replace(",", ""))
+                if units[i] in UNIT:
+                    v *= UNIT[units[i]]
+            except ValueError:
+                pass
+            m[h] = v
+    return m
+
+
+def source_mix(rep):
+    rows = list(csv.reader(io.StringIO(ncu("-i", str(rep), "--page", "source", "--csv", "--print-source", "sass"))))
+    hdr, out = None, []
+    for r in rows:
+        if r and r[0] == "Address":
+            if hdr is not None:
+                break
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr):
+            out.append(r)
+    ix = {h: i for i, h in enumerate(hdr)}
+    mix, stalls, total = collections.Counter(), collections.Counter(), 0
+    for r in out:
+        src = r[ix["Source"]].strip()
+        mm = re.match(r"(@!?U?P[0-9T]+\s+)?([A-Z0-9_]+)", src)
+        op = mm.group(2) if mm else src
+        ex = int(r[ix["Instructions Executed"]])
+        mix[op] += ex
+        total += ex
+        for h in hdr:
+            if h.startswith("stall_") and "Not Issued" not in h:
+                stalls[h[6:]] += int(r[ix[h]])
+    s = sum(stalls.values()) or 1
+    return ({k: v for k, v in mix.most_common(24)}, total,
+            {k: round(100.0 * v / s, 1) for k, v in stalls.most_common(10)})
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    OUT.mkdir(exist_ok=True)
+    traffic = {}
+    tp = OUT / "traffic.json"
+    if tp.exists():
+        traffic = json.loads(tp.read_text())
+    for sf in (7, 10, 12):
+        rep = SRC / f"prof_sf{sf}.ncu-rep"
+        if not rep.exists():
+            continue
+        m = raw_metrics(rep)
+        mix, total, stalls = source_mix(rep)
+        n = 1 << sf
+        windows = 65536 if sf == 7 else 16384
+        dram = m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0)
+        traffic[f"sf{sf}"] = dram
+        summ = {
+            "what": f"ncu --set full --clock-control none, one launch of demod_fused_kernel<SF={sf}> "
+                    f"({windows} windows) inside `python bench.py --sf {sf} --windows {windows}`; "
+                    "per-launch numbers are cold-cache and serialised (no PDL overlap): compare shares, not absolutes",
+            "metrics": m,
+            "algorithmic_bytes": windows * (8 * n + 16),
+            "dram_bytes_per_launch": dram,
+            "warp_instructions_executed": total,
+            "lane_instructions_per_sample": round(total * 32 / (windows * n), 2),
+            "instruction_mix_top": mix,
+            "stall_reasons_pct_of_samples": stalls,
+        }
+        (OUT / f"{tag}_ncu_sf{sf}.json").write_text(json.dumps(summ, indent=1))
+        print(f"sf{sf}: {m.get('gpu__time_duration.sum')} ns? dram {dram/1e6:.2f} MB, "
+              f"{summ['lane_instructions_per_sample']} lane-instr/sample, issue "
+              f"{m.get('smsp__issue_active.avg.pct_of_peak_sustained_active')}%")
+    tp.write_text(json.dumps(traffic, indent=1))
+    lc = SRC / "launches_sf7.csv"
+    if lc.exists():
+        shutil.copy(lc, OUT / f"{tag}_launches_sf7.csv")
+        # share of the step: all launches inside the timed region are ours
+        rows = [r for r in csv.reader(open(lc)) if len(r) > 5 and r[0].isdigit()]
+        by = collections.Counter()
+        for r in rows:
+            try:
+                by[r[4][:60]] += float(r[-1].replace(",", ""))
+            except ValueError:
+                pass
+        tot = sum(by.values()) or 1
+        lines = [f"{k}: {v/1e3:.1f} us total, {100*v/tot:.1f}% of all profiled launches" for k, v in by.most_common(8)]
+        (OUT / f"{tag}_launches_sf7_summary.txt").write_text("\n".join(lines) + "\n")
+        print("\n".join(lines[:4]))
+
+
+if __name__ == "__main__":
+    main()
