@@ -310,11 +310,13 @@ def main():
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------------------
     Ke = args.e2e_steps or min(K, 100)
-    host_bufs = []
+    host_bufs, pinned = [], []
     for b in range(min(2, nbuf)):
-        hb = torch.empty((nw, n), dtype=torch.complex64).pin_memory()
-        hb.copy_(bufs[b])
-        host_bufs.append(hb)
+        # page-locked buffers from the library's own allocator (what a block's buffer manager uses)
+        pa = m.PinnedArray((nw, n))
+        pa.array[...] = bufs[b].cpu().numpy()
+        pinned.append(pa)
+        host_bufs.append(pa.array)
     host_out = np.empty(nw, m.RESULT_DTYPE)
     for i in range(3):
         d.demod_host(host_bufs[i % len(host_bufs)], nw, out=host_out)
@@ -349,7 +351,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world >= 1:
         cores = len(os.sched_getaffinity(0))
-        host_np = host_bufs[0].numpy()
+        host_np = host_bufs[0]
         kind, sample, v, res = cpu_reference(sf, host_np, cores, budget_s=4.0)
         cpu = {"value": v, "unit": "Msymbols/s", "cores": cores, "kind": kind,
                "sample": f"first {sample} windows of the step's batch, {cores} threads, one LoRaDetector per thread"}
@@ -366,7 +368,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Msymbols/s", "h2d_bytes_per_step": step_bytes,
                 "d2h_bytes_per_step": nw * 32, "steps": Ke, "symbols_ok": e2e_ok,
-                "api": "lorab200_demod_host (pinned host buffers, H2D + kernel + D2H + host finalise per step)"},
+                "api": "lorab200_demod_host (host buffers from lorab200_alloc_pinned; H2D + kernel + D2H + host finalise per step)"},
         "gpu_launches": int(launches_per_graph),
         "roofline": roof,
         "cpu_baseline": cpu,

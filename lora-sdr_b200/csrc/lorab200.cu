@@ -8,6 +8,10 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -34,7 +38,75 @@ struct DevBuf {
 
 } // namespace
 
+namespace {
+// A few persistent helper threads per context for the host-side finalisation of large
+// batches (libm log10f/hypotf per window); created on first use, joined in destroy.
+class Helpers {
+public:
+    ~Helpers() { stop(); }
+    void ensure(size_t n)
+    {
+        while (th_.size() < n) th_.emplace_back([this] { loop(); });
+    }
+    // run fn(i) for i in [0, n) on the helpers plus the calling thread
+    void parallel(size_t n, const std::function<void(size_t)> &fn)
+    {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            fn_ = &fn; next_ = 0; total_ = n; busy_ = th_.size(); ++gen_;
+        }
+        cv_.notify_all();
+        for (;;) {
+            const size_t i = next_.fetch_add(1);
+            if (i >= n) break;
+            fn(i);
+        }
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return busy_ == 0; });
+        fn_ = nullptr;
+    }
+    void stop()
+    {
+        { std::lock_guard<std::mutex> l(m_); quit_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+        th_.clear();
+    }
+private:
+    void loop()
+    {
+        unsigned long seen = 0;
+        for (;;) {
+            const std::function<void(size_t)> *fn;
+            size_t total;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (quit_) return;
+                fn = fn_; total = total_;
+            }
+            for (;;) {
+                const size_t i = next_.fetch_add(1);
+                if (i >= total) break;
+                (*fn)(i);
+            }
+            { std::lock_guard<std::mutex> l(m_); if (--busy_ == 0) done_.notify_all(); }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(size_t)> *fn_ = nullptr;
+    std::atomic<size_t> next_{0};
+    size_t total_ = 0, busy_ = 0;
+    unsigned long gen_ = 0;
+    bool quit_ = false;
+};
+} // namespace
+
 struct lorab200_ctx {
+    Helpers helpers;
     int device = 0;
     int sf = 0;
     size_t n = 0;
@@ -421,8 +493,12 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
 
     // Software pipeline over chunks of windows on two streams: the H2D copy of chunk
     // i+1 overlaps the kernel and the D2H copy of chunk i, and the host-side
-    // finalisation (libm) of chunk i-1.  A chunk is ~4 MiB of IQ, at most 64 chunks.
-    size_t cw = (size_t(4) << 20) / (n * sizeof(float2));
+    // finalisation (libm) of earlier chunks; at most 64 chunks.
+    // chunk = 2048 windows (the unit one thread finalises in ~0.1 ms), but between 2 and 16 MiB of IQ
+    size_t cw = 2048;
+    const size_t wbytes = n * sizeof(float2);
+    if (cw * wbytes < (size_t(2) << 20)) cw = (size_t(2) << 20) / wbytes;
+    if (cw * wbytes > (size_t(16) << 20)) cw = (size_t(16) << 20) / wbytes;
     if (cw == 0) cw = 1;
     if ((n_windows + cw - 1) / cw > 64) cw = (n_windows + 63) / 64;
     // a walking fine-tune index is pre-rolled through per-context scratch: no pipelining
@@ -459,34 +535,24 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     // Host-side finalisation (libm log10f/hypotf, LoRaDetector.hpp:50-61) of chunk k as
     // soon as its results have landed, while later chunks are still in flight.  Large
     // batches split the chunks over a few threads so this stays hidden behind the H2D copy.
-    auto finish = [&](size_t first, size_t step) -> cudaError_t {
-        cudaSetDevice(c->device);
-        for (size_t k = first; k < n_chunks; k += step) {
-            cudaError_t e = cudaEventSynchronize(c->chunk_done[k % 64]);
-            if (e != cudaSuccess) return e;
-            const size_t p0 = k * cw, p1 = (p0 + cw < n_windows) ? p0 + cw : n_windows;
-            finalize_host(h_raw + p0, p1 - p0, c->pscale, out + p0);
-        }
-        return cudaSuccess;
+    std::atomic<int> ferr_code{int(cudaSuccess)};
+    const std::function<void(size_t)> finish = [&](size_t k) {
+        cudaError_t e = cudaEventSynchronize(c->chunk_done[k % 64]);
+        if (e != cudaSuccess) { ferr_code = int(e); return; }
+        const size_t p0 = k * cw, p1 = (p0 + cw < n_windows) ? p0 + cw : n_windows;
+        finalize_host(h_raw + p0, p1 - p0, c->pscale, out + p0);
     };
-    size_t n_thr = 1;
     if (n_windows >= 16384 && n_chunks >= 4) {
-        n_thr = std::thread::hardware_concurrency() / 4;
+        size_t n_thr = std::thread::hardware_concurrency() / 4;
         if (n_thr > 8) n_thr = 8;
         if (n_thr > n_chunks) n_thr = n_chunks;
-        if (n_thr < 1) n_thr = 1;
-    }
-    cudaError_t ferr = cudaSuccess;
-    if (n_thr == 1) {
-        ferr = finish(0, 1);
+        if (n_thr < 2) n_thr = 2;
+        c->helpers.ensure(n_thr - 1);
+        c->helpers.parallel(n_chunks, finish);   // chunks are taken in order, so in completion order
     } else {
-        std::vector<std::thread> th;
-        std::vector<cudaError_t> errs(n_thr, cudaSuccess);
-        for (size_t t = 1; t < n_thr; ++t) th.emplace_back([&, t] { errs[t] = finish(t, n_thr); });
-        errs[0] = finish(0, n_thr);
-        for (auto &x : th) x.join();
-        for (auto e : errs) if (e != cudaSuccess) ferr = e;
+        for (size_t k = 0; k < n_chunks; ++k) finish(k);
     }
+    const cudaError_t ferr = cudaError_t(ferr_code.load());
     if (ferr != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "cudaEventSynchronize(chunk)", ferr);
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream2));
