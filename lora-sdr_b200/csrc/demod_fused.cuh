@@ -281,14 +281,42 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
     // previous demod kernel in the stream.
     pdl_launch_dependents();
     const uint32_t cbar = smem_base + uint32_t(C::GROUPS * STAGES) * 8u; // chirp-table barrier (CTA wide)
+
+    auto issue = [&](uint32_t k, int s) {
+        // TMA the whole tile k of this group (contiguous in HBM: stride == N)
+        const uint32_t tile = tile0 + k;
+        const uint32_t w0 = tile * WPT;
+        uint32_t nw = n_windows - w0;
+        if (nw > WPT) nw = WPT;
+        const uint32_t bytes = nw * N * 8u;
+        mbar_expect_tx(bar0 + s * 8, bytes);
+        tma_load_1d(gbase + s * C::STAGE_BYTES, p.iq + size_t(w0) * N, bytes, bar0 + s * 8);
+    };
+
     if (tg == 0) {
+        // the group's own thread 0 initialises its stage barriers and may use them at once;
+        // the other threads only touch them after the __syncthreads below
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(bar0 + s * 8, 1);
         if (tid == 0 && C::CHIRP_SMEM) mbar_init(cbar, 1);
         fence_proxy_async(); // make the inits visible to the async (TMA) proxy
+        if (tid == 0 && C::CHIRP_SMEM) {
+            // chirp table -> shared memory by TMA (same linear layout as a window)
+            mbar_expect_tx(cbar, uint32_t(N) * 8u);
+            tma_load_1d(chirp_s, p.chirp, uint32_t(N) * 8u, cbar);
+        }
+        // With LORAB200_FLAG_INPUT_STABLE the caller guarantees that the IQ batch was not
+        // produced by the kernel launched just before this one on the stream (a streaming
+        // receiver's double buffering), so the first TMA loads start right here, before the
+        // prior grid has drained; the results are still only written after the wait below.
+        if (p.early_iq) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s)
+                if (uint32_t(s) < my_tiles) issue(s, s);
+        }
     }
-    // twiddles of the radix-16 passes (registers for the whole persistent loop); issued
-    // first so their latency overlaps the barrier and the first TMA round trip
+    // twiddles of the radix-16 passes (registers for the whole persistent loop); their global
+    // loads overlap the barrier and the first TMA round trip
     float2 tw1a[3], tw1b[4][3];
     float2 tw2a[3], tw2b[4][3];
     // Thread coordinates of the radix-16 passes.  Two passes: lo1 = t (hi1 = 0).  Three
@@ -305,33 +333,6 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
     if constexpr (C::NP == 3) load_pass_tw<SF, B0 + 4>(p.tw, tL, tw2a, tw2b);
 
     __syncthreads(); // barrier inits visible CTA-wide (the chirp barrier is shared by all groups)
-    if constexpr (C::CHIRP_SMEM) {
-        // chirp table -> shared memory by TMA (same linear layout as a window)
-        if (tid == 0) {
-            mbar_expect_tx(cbar, uint32_t(N) * 8u);
-            tma_load_1d(chirp_s, p.chirp, uint32_t(N) * 8u, cbar);
-        }
-    }
-
-    auto issue = [&](uint32_t k, int s) {
-        // TMA the whole tile k of this group (contiguous in HBM: stride == N)
-        const uint32_t tile = tile0 + k;
-        const uint32_t w0 = tile * WPT;
-        uint32_t nw = n_windows - w0;
-        if (nw > WPT) nw = WPT;
-        const uint32_t bytes = nw * N * 8u;
-        mbar_expect_tx(bar0 + s * 8, bytes);
-        tma_load_1d(gbase + s * C::STAGE_BYTES, p.iq + size_t(w0) * N, bytes, bar0 + s * 8);
-    };
-    // With LORAB200_FLAG_INPUT_STABLE the caller guarantees that the IQ batch was not
-    // produced by the kernel launched just before this one on the stream (a streaming
-    // receiver's double buffering), so the first TMA loads may start before the prior
-    // grid has drained; the results are still only written after the wait.
-    if (p.early_iq && tg == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s)
-            if (uint32_t(s) < my_tiles) issue(s, s);
-    }
     pdl_wait_prior_grid(); // from here on: the IQ batch (unless stable) and the result buffers
     if (!p.early_iq && tg == 0) {
 #pragma unroll

@@ -66,3 +66,25 @@ def test_bad_arguments_rejected_before_touching_cuda(lib):
     assert L.lorab200_create(None, 0, 7, 0) == -1
     assert L.lorab200_demod_dev(None, None, 0, 0, 0, None, None, None, None, None) == -1
     L.lorab200_destroy(None)  # must be a no-op
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/lorab200.h must be consumable by a C compiler (the drop-in boundary is a C ABI)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    src = tmp_path / "use.c"
+    src.write_text(
+        '#include "lorab200.h"\n'
+        "int use(void) {\n"
+        "    lorab200_ctx *c = 0; lorab200_result r[4]; lorab200_fine f = {0, 0.0f};\n"
+        "    float iq[2 * 128 * 4];\n"
+        "    if (lorab200_create(&c, 0, 7, LORAB200_FLAG_DEFAULT) != LORAB200_OK) return 1;\n"
+        "    int st = lorab200_demod_host(c, iq, 4, 128, LORAB200_TABLE_UP, &f, r, 0, 0);\n"
+        "    lorab200_destroy(c);\n"
+        "    return st + (int)sizeof(lorab200_result) - 16;\n"
+        "}\n")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only",
+                        f"-I{ROOT / 'include'}", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
