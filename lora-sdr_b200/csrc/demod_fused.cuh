@@ -578,8 +578,11 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
                 for (int q = 1; q < G / 32; ++q) { sum += red_sum[q]; argmax_merge(bv, bi, red_val[q], red_idx[q]); }
             }
             // neighbours of the peak, (bi-1) mod N and (bi+1) mod N, live in other threads' registers
-            const int jl = bi > 0 ? bi - 1 : N - 1, jr = bi < N - 1 ? bi + 1 : 0;
-            const int tl = jl & (G - 1), yl = jl / G, tr = jr & (G - 1), yr = jr / G;
+            // (cyclic neighbours, LoRaDetector.hpp:56-57: N is a power of two, so the wrap is a mask)
+            const unsigned jl = (unsigned(bi) + unsigned(N - 1)) & unsigned(N - 1);
+            const unsigned jr = (unsigned(bi) + 1u) & unsigned(N - 1);
+            const int tl = int(jl & unsigned(G - 1)), yl = int(jl >> (SF - 4));
+            const int tr = int(jr & unsigned(G - 1)), yr = int(jr >> (SF - 4));
             const c64 nbv = pick16(r, tL == tl ? yl : yr);
             // the record of this window is assembled in shared memory by the three lanes that
             // own its pieces; it is read back at the next flush (after a group-wide sync)
