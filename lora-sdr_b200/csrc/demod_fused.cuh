@@ -283,14 +283,21 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
     const uint32_t cbar = smem_base + uint32_t(C::GROUPS * STAGES) * 8u; // chirp-table barrier (CTA wide)
 
     auto issue = [&](uint32_t k, int s) {
-        // TMA the whole tile k of this group (contiguous in HBM: stride == N)
+        // TMA tile k of this group into stage s: one bulk copy when the batch is dense
+        // (stride == N), one per window otherwise (sliding / overlapping windows)
         const uint32_t tile = tile0 + k;
         const uint32_t w0 = tile * WPT;
         uint32_t nw = n_windows - w0;
         if (nw > WPT) nw = WPT;
         const uint32_t bytes = nw * N * 8u;
         mbar_expect_tx(bar0 + s * 8, bytes);
-        tma_load_1d(gbase + s * C::STAGE_BYTES, p.iq + size_t(w0) * N, bytes, bar0 + s * 8);
+        if (WPT == 1 || p.stride == N) {
+            tma_load_1d(gbase + s * C::STAGE_BYTES, p.iq + size_t(w0) * p.stride, bytes, bar0 + s * 8);
+        } else {
+            for (uint32_t i = 0; i < nw; ++i)
+                tma_load_1d(gbase + s * C::STAGE_BYTES + i * N * 8u, p.iq + size_t(w0 + i) * p.stride,
+                            N * 8u, bar0 + s * 8);
+        }
     };
 
     if (tg == 0) {
@@ -608,8 +615,9 @@ inline bool fused_applicable(int sf, const DemodParams &p)
 {
     if (sf < 7 || sf > 12) return false;
     const unsigned long long n = 1ull << sf;
-    if (p.stride != n && p.n_windows > 1) return false;              // dense batches only
-    if ((reinterpret_cast<uintptr_t>(p.iq) & 15u) != 0) return false; // TMA needs 16-byte alignment
+    (void)n;
+    if ((reinterpret_cast<uintptr_t>(p.iq) & 15u) != 0) return false; // TMA needs 16-byte aligned sources:
+    if ((p.stride & 1ull) != 0 && p.n_windows > 1) return false;      // base aligned and an even sample stride
     if (p.n_windows >= (1ull << 31)) return false;
     if (p.fine != nullptr && p.fine_step != 0.0f) return false;       // walking fine index: simple kernel
     return true;

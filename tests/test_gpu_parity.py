@@ -104,6 +104,32 @@ def test_stride_offset_and_down_table(lib, oracle, cuda_ok, sf, flags):
     d.close()
 
 
+@pytest.mark.parametrize("stride_of_n", [lambda n: n + 2, lambda n: n // 2, lambda n: 2, lambda n: 3 * n],
+                         ids=["n+2", "n/2", "2", "3n"])
+@pytest.mark.parametrize("sf", [7, 8, 10, 12])
+def test_fused_kernel_strided_and_overlapping_windows(lib, oracle, cuda_ok, sf, stride_of_n):
+    """Even sample strides (16-byte aligned windows) stay on the TMA path: sliding / overlapping /
+    gapped windows, e.g. a preamble search at every second sample."""
+    n = 1 << sf
+    stride = stride_of_n(n)
+    nw = 45 if sf <= 8 else 13
+    rng = np.random.default_rng(sf + stride)
+    total = (nw - 1) * stride + n
+    buf = (rng.standard_normal(total) + 1j * rng.standard_normal(total)).astype(np.complex64)
+    d = lib.Demod(sf)
+    up = d.table(lib.TABLE_UP)
+    exp, _, efft, edec = oracle.demod_windows(sf, buf, nw, up, stride=stride, want_fft=True, want_dec=True)
+    out, _, fft, dec = d.demod_dev(_dev(buf), nw, stride=stride, want_fft=True, want_dec=True)
+    assert d.last_kernel.startswith("fused"), d.last_kernel
+    _check_records(lib.results_to_numpy(out), exp, exact_power=False, sf=sf)
+    assert same_values(fft.cpu().numpy(), efft) and same_values(dec.cpu().numpy(), edec)
+    out2, _, _, _ = d.demod_dev(_dev(buf), nw, stride=stride)          # the non-debug variant
+    _check_records(lib.results_to_numpy(out2), exp, exact_power=False, sf=sf)
+    got_h, _, _, _ = d.demod_host(buf, nw, stride=stride)
+    _check_records(got_h, exp, exact_power=True, sf=sf)
+    d.close()
+
+
 @pytest.mark.parametrize("flags", [1, 0], ids=["simple", "default"])
 @pytest.mark.parametrize("step", [0.0, 1.28, -3.7, 55.001, 3.001])
 @pytest.mark.parametrize("sf", [7, 9, 12])
