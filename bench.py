@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (0 = min(K, 100))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--simple", action="store_true", help="force the simple (non-fused) kernel")
+    ap.add_argument("--no-input-stable", action="store_true",
+                    help="do not set LORAB200_FLAG_INPUT_STABLE (first loads wait for the previous launch to drain)")
     return ap.parse_args()
 
 
@@ -238,7 +240,8 @@ def main():
     n = 1 << sf
     # the synthetic batches are resident and never rewritten: let consecutive launches overlap
     # their first loads with the previous launch's tail (LORAB200_FLAG_INPUT_STABLE)
-    d = m.Demod(sf, device=local, flags=m.FLAG_SIMPLE_ONLY if args.simple else m.FLAG_INPUT_STABLE)
+    d = m.Demod(sf, device=local, flags=m.FLAG_SIMPLE_ONLY if args.simple else
+                (m.FLAG_DEFAULT if args.no_input_stable else m.FLAG_INPUT_STABLE))
 
     # ---- tables: rank 0's copy is broadcast over NCCL (the only collective on this path) -------
     if world > 1:

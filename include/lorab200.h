@@ -127,6 +127,13 @@ int lorab200_tables_sync_from_dev(lorab200_ctx *ctx);
 size_t lorab200_table_len(int sf, int which);
 int lorab200_build_table(int sf, int which, float *out);
 
+/* Advance the fine-tune index recurrence (LoRaDemod.cpp:160-162) by n_samples steps in
+ * closed form -- exactly what n_samples applications of
+ *     index = int(float(index) - step); wrap once into [0, N*128)
+ * give, in O(1) per wrap of the table instead of O(n_samples).  Host only, no context.
+ * Returns the new index, or a negative status for bad arguments (|step| must be < N*128). */
+int32_t lorab200_fine_advance(int sf, int32_t index, float step, uint64_t n_samples);
+
 /* ChirpGenerator.hpp:21-47 genChirp<float> on the host (bit-identical recipe);
  * the signal generator the modulator and TestDetector use.  Returns the number
  * of samples generated (NN), or a negative status. */

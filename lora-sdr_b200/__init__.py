@@ -50,7 +50,7 @@ EXPORTS = [
     "lorab200_table_dev", "lorab200_set_table", "lorab200_tables_sync_from_dev",
     "lorab200_gen_chirp", "lorab200_demod_dev", "lorab200_demod_host", "lorab200_pack_symbols",
     "lorab200_kernel_launches", "lorab200_last_kernel", "lorab200_alloc_pinned",
-    "lorab200_free_pinned", "lorab200_table_len", "lorab200_build_table",
+    "lorab200_free_pinned", "lorab200_table_len", "lorab200_build_table", "lorab200_fine_advance",
 ]
 
 
@@ -133,6 +133,8 @@ def load_library() -> C.CDLL:
     L.lorab200_table_len.argtypes = [C.c_int, C.c_int]
     L.lorab200_table_len.restype = sz
     L.lorab200_build_table.argtypes = [C.c_int, C.c_int, vp]
+    L.lorab200_fine_advance.argtypes = [C.c_int, C.c_int32, C.c_float, C.c_uint64]
+    L.lorab200_fine_advance.restype = C.c_int32
     L.lorab200_gen_chirp.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float,
                                      C.POINTER(C.c_float)]
     L.lorab200_demod_dev.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp, vp, vp, vp]
@@ -169,6 +171,14 @@ def gen_chirp(N: int, ovs: int, NN: int, f0: float, down: bool, ampl: float, pha
     if n < 0:
         raise Lorab200Error(L.lorab200_strerror(n).decode())
     return out[:n], float(ph.value)
+
+
+def fine_advance(sf: int, index: int, step: float, n_samples: int) -> int:
+    """Closed-form advance of the fine-tune index recurrence (LoRaDemod.cpp:160-162)."""
+    r = load_library().lorab200_fine_advance(sf, int(index), C.c_float(step), int(n_samples))
+    if r < 0:
+        raise Lorab200Error("bad arguments to lorab200_fine_advance")
+    return int(r)
 
 
 def build_table(sf: int, which: int) -> np.ndarray:

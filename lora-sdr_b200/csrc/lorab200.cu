@@ -22,6 +22,7 @@
 #ifndef LORAB200_NO_FUSED
 #include "demod_fused.cuh"
 #endif
+#include "fine_walk.h"
 #include "finalize.h"
 #include "tables.h"
 
@@ -216,20 +217,15 @@ cudaError_t launch_simple(int sf, const DemodParams &p, cudaStream_t s, int sm_c
     }
 }
 
-// Pre-roll the fine-tune index recurrence (LoRaDemod.cpp:160-162) to the start
-// of every window; sequential by nature, O(N*W) integer/float steps on the host.
+// Fine-tune index (LoRaDemod.cpp:160-162) at the start of every window, in closed form
+// (fine_walk.h): O(windows), not O(samples).
 void roll_fine(int32_t idx, float step, int32_t len, size_t n, size_t n_windows,
                int32_t *idx0, int32_t *idx_end)
 {
+    const FineWalk walk(len, step);
     for (size_t w = 0; w < n_windows; ++w) {
         idx0[w] = idx;
-        if (step != 0.0f) {
-            for (size_t i = 0; i < n; ++i) {
-                idx = int32_t(float(idx) - step);
-                if (idx < 0) idx += len;
-                else if (idx >= len) idx -= len;
-            }
-        }
+        if (step != 0.0f) idx = walk.advance(idx, n);
     }
     *idx_end = idx;
 }
@@ -265,6 +261,8 @@ int run_demod(lorab200_ctx *c, const void *iq_dev, size_t n_windows, size_t stri
     if (fine) {
         if (fine->index < 0 || fine->index >= p.fine_len)
             return fail(c, LORAB200_ERR_INVALID, "fine->index out of [0, N*128)");
+        if (!(fine->step > -float(p.fine_len) && fine->step < float(p.fine_len)))
+            return fail(c, LORAB200_ERR_INVALID, "|fine->step| must be below N*128");
         p.fine = c->d_table[LORAB200_TABLE_FINE];
         p.fine_step = fine->step;
     }
@@ -452,6 +450,15 @@ int lorab200_build_table(int sf, int which, float *out)
     }
     std::memcpy(out, a.data(), a.size() * sizeof(cfloat));
     return LORAB200_OK;
+}
+
+int32_t lorab200_fine_advance(int sf, int32_t index, float step, uint64_t n_samples)
+{
+    if (sf < 7 || sf > 12) return LORAB200_ERR_INVALID;
+    const int32_t len = int32_t((size_t(1) << sf) * kFineSteps);
+    if (index < 0 || index >= len || !(step > -float(len) && step < float(len))) return LORAB200_ERR_INVALID;
+    if (step == 0.0f) return index;
+    return FineWalk(len, step).advance(index, n_samples);
 }
 
 int lorab200_gen_chirp(float *samps, int N, int ovs, int NN, float f0, int down, float ampl,

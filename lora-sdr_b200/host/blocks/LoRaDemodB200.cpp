@@ -89,6 +89,7 @@ class LoRaDemodB200 : public Pothos::Block
 public:
     LoRaDemodB200(const size_t sf):
         N(size_t(1) << sf),
+        _sf(int(sf)),
         _fineSteps(128),
         _ctx(nullptr),
         _sync(0x12),
@@ -393,19 +394,14 @@ private:
         Window win;
     } _cache;
 
-    //one step of LoRaDemod.cpp:160-162 for a whole window
+    //LoRaDemod.cpp:160-162 advanced over a whole window, in closed form (lorab200_fine_advance)
     int rollIndex(int idx, const float ffe) const
     {
         const float step = ffe * _fineSteps;
         if (step == 0.0f) return idx;
-        const int len = int(N * _fineSteps);
-        for (size_t i = 0; i < N; i++)
-        {
-            idx = int(float(idx) - step);
-            if (idx < 0) idx += len;
-            else if (idx >= len) idx -= len;
-        }
-        return idx;
+        const int32_t r = lorab200_fine_advance(_sf, idx, step, N);
+        if (r < 0) throw Pothos::Exception("LoRaDemodB200::work()", "fine tune state out of range");
+        return r;
     }
 
     //! result for the window that starts `ahead` windows after sample `off` under the current state
@@ -483,6 +479,7 @@ private:
 
     //configuration
     const size_t N;
+    const int _sf;
     const size_t _fineSteps;
     lorab200_ctx *_ctx;
     unsigned char _sync;
