@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (0 = min(K, 100))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--simple", action="store_true", help="force the simple (non-fused) kernel")
+    ap.add_argument("--fine-step", type=float, default=None,
+                    help="demodulate with a walking fine-tune index of this step per sample "
+                         "(LoRaDemod.cpp:157-166 after sync); default: the detector-only form")
     ap.add_argument("--no-input-stable", action="store_true",
                     help="do not set LORAB200_FLAG_INPUT_STABLE (first loads wait for the previous launch to drain)")
     return ap.parse_args()
@@ -267,17 +270,19 @@ def main():
     # ---- correctness spot check on this rank (sampled windows vs the CPU oracle) -------------------
     parity = spot_check(m, d, sf, bufs[0], syms[0], out)
 
+    fine = None if args.fine_step is None else (1234, float(args.fine_step))
+
     # ---- device-resident timing: K steps in one CUDA graph ----------------------------------------------
     stream = torch.cuda.Stream(device=device)
     with torch.cuda.stream(stream):
         for i in range(max(3, W)):
-            d.demod_dev(bufs[i % nbuf], nw, out=out, stream=stream.cuda_stream)
+            d.demod_dev(bufs[i % nbuf], nw, out=out, stream=stream.cuda_stream, fine=fine)
         stream.synchronize()
         graph = torch.cuda.CUDAGraph()
         launches0 = d.kernel_launches
         with torch.cuda.graph(graph, stream=stream):
             for i in range(K):
-                d.demod_dev(bufs[i % nbuf], nw, out=out, stream=torch.cuda.current_stream().cuda_stream)
+                d.demod_dev(bufs[i % nbuf], nw, out=out, stream=torch.cuda.current_stream().cuda_stream, fine=fine)
         launches_per_graph = d.kernel_launches - launches0
         graph.replay()                       # warm replay (graph upload)
         stream.synchronize()
@@ -367,6 +372,7 @@ def main():
                    "l2": f"inputs rotate over {nbuf} distinct {step_bytes >> 20} MiB buffers "
                          f"({nbuf * step_bytes >> 20} MiB > 3x L2), so every step streams from HBM",
                    "timing": "K steps captured in one CUDA graph (programmatic dependent launch between steps, LORAB200_FLAG_INPUT_STABLE), CUDA events on the launching stream",
+                   "fine_step": args.fine_step,
                    "parity_spot_check": parity, "sharding": "windows block-partitioned per rank, no data-path collective"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Msymbols/s", "h2d_bytes_per_step": step_bytes,

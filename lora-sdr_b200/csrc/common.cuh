@@ -32,7 +32,9 @@ struct DemodParams {
     unsigned long long stride; // in samples
     const float2 *chirp;      // N entries (up or down table)
     const float2 *fine;       // N*128 entries or nullptr
-    const int32_t *fine_idx0; // per-window start index (device) or nullptr
+    const int32_t *fine_x16;  // walking index: state at every 16th dechirped sample of the batch
+                              // (fine_prefix.cuh), [n_windows * N/16] on the device; nullptr if step == 0
+    int   fine_index0;        // the constant index when fine_step == 0
     float fine_step;          // _finefreqError * _fineSteps
     int   fine_len;           // N*128
     const float2 *tw;         // kissfft twiddles, N entries

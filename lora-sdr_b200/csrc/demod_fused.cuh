@@ -86,6 +86,10 @@ struct FusedCfg {
     // the planned number of CTAs must fit in one SM: 228 KB per SM, 1 KB reserved per CTA
     static_assert(CTAS_PER_SM * (SMEM_BYTES + 1024) <= 233472, "shared memory budget");
     static_assert(RAWCAP % WPT == 0 && RAWCAP <= 32, "RAWCAP");
+    // FINE_WALK parks N fine-tune indices per window in the exchange buffer while it is idle:
+    // 32-bit words at fine_pad(j); window stride chosen so two windows of a warp use disjoint banks
+    static constexpr int FINE_WSTRIDE = N + N / 8 + (SF == 8 ? 16 : 0); // words
+    static_assert(WPT * FINE_WSTRIDE * 4 <= X_BYTES && (FINE_WSTRIDE * 4) % 16 == 0, "fine index area");
 };
 
 // Uniform twiddles used inside pass 0 (kissfft.hh:141-143 with m = 2 or 4): passed by
@@ -235,13 +239,27 @@ __device__ __forceinline__ c64 pick16(const c64 (&r)[16], int slot)
     return (slot & 8) ? c[1] : c[0];
 }
 
-// DBG  : also write the fft / dec debug dumps (p.fft, p.dec may be null individually)
-// FINE0: multiply every dechirped sample by one constant fine-tune phasor (the
-//        LoRaDemod.cpp:159 form when _finefreqError == 0: index constant over the batch)
-template <int SF, bool DBG, bool FINE0>
+// DBG : also write the fft / dec debug dumps (p.fft, p.dec may be null individually)
+// FINE: fine-tune multiply of LoRaDemod.cpp:159
+//   FINE_NONE  no fine-tune table (the detector-only form, TestDetector.cpp)
+//   FINE_CONST one constant phasor for the whole batch (_finefreqError == 0: the index never moves)
+//   FINE_WALK  the index walks once per sample (LoRaDemod.cpp:160-162).  The state at the start
+//              of every 16-sample chunk comes from the pointer-jumping prefix (fine_prefix.cuh);
+//              thread t of a window walks chunk t with the literal recurrence and parks the 16
+//              indices in the (idle) exchange buffer, from where every thread picks up the
+//              indices of its own pass-0 samples; the phasors are gathered from the table in L2.
+enum { FINE_NONE = 0, FINE_CONST = 1, FINE_WALK = 2 };
+
+// word offset of fine index j inside a window's exchange area: +4 words every 32 so that the
+// 64-byte per-thread chunks are written conflict free with 128-bit stores
+__host__ __device__ constexpr int fine_pad(int j) { return j + 4 * (j >> 5); }
+__device__ __forceinline__ int fine_pad_dyn(int j) { return j + 4 * (j >> 5); }
+
+template <int SF, bool DBG, int FINE>
 __global__ void __launch_bounds__(256, FusedCfg<SF>::CTAS_PER_SM)
 demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_phasor)
 {
+    constexpr bool FINE0 = (FINE == FINE_CONST);
     using C = FusedCfg<SF>;
     constexpr int N = C::N, B0 = C::B0, R0 = C::R0, E = C::E, G = C::G, GROUP = C::GROUP;
     constexpr int WPT = C::WPT, STAGES = C::STAGES;
@@ -263,8 +281,7 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
     const uint32_t xbase = gbase + STAGES * C::STAGE_BYTES;
     RawResult *rawbuf = reinterpret_cast<RawResult *>(gptr + STAGES * C::STAGE_BYTES + C::X_BYTES);
     double *red_sum = reinterpret_cast<double *>(gptr + STAGES * C::STAGE_BYTES + C::X_BYTES + C::RAW_BYTES);
-    float *red_val = reinterpret_cast<float *>(red_sum + 8);   // 8 doubles | 8 floats | 8 ints | 2 float2
-    int *red_idx = reinterpret_cast<int *>(red_val + 8);
+    // (red_sum: up to 8 cross-warp partials of 16 bytes: {double sum, float bits, int index})
 
     // ---- this group's contiguous range of tiles --------------------------------------------
     const uint32_t n_windows = uint32_t(p.n_windows);
@@ -405,6 +422,42 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
                     }
             }
 
+            // ---- walking fine-tune index: this thread's 16 table indices ---------------------------
+            int fidx[FINE == FINE_WALK ? 16 : 1];
+            if constexpr (FINE == FINE_WALK) {
+                group_sync<GROUP>(grp); // the previous tile's gathers from X are done group-wide
+                int x = live ? __ldg(p.fine_x16 + size_t(w) * G + t) : 0;
+                const uint32_t fx = xbase + uint32_t(wsub) * C::FINE_WSTRIDE * 4u; // this window's index area
+                const uint32_t cbase = fx + uint32_t(fine_pad_dyn(16 * t)) * 4u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { v[i] = x; x = fine_next(x, p.fine_step, p.fine_len); }
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + q * 16u),
+                                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+                }
+                group_sync<GROUP>(grp);
+                // gather in pass-0 order.  j = jc + ilow(t): for every SF the constant part jc and
+                // the thread part never carry into each other's 32-block, so the padded address is
+                // "thread base + immediate" (tools/layout_model.py checks it and the bank conflicts)
+                const uint32_t gb = fx + uint32_t(fine_pad_dyn(E == 1 ? t : 2 * t)) * 4u;
+                if constexpr (E == 1) {
+#pragma unroll
+                    for (int c = 0; c < R0; ++c)
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(fidx[c])
+                                     : "r"(gb + uint32_t(fine_pad((N / R0) * c)) * 4u));
+                } else {
+#pragma unroll
+                    for (int eh = 0; eh < E / 2; ++eh)
+#pragma unroll
+                        for (int c = 0; c < R0; ++c)
+                            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];"
+                                         : "=r"(fidx[(2 * eh) * R0 + c]), "=r"(fidx[(2 * eh + 1) * R0 + c])
+                                         : "r"(gb + uint32_t(fine_pad(eh * 2 * G + (N / R0) * c)) * 4u));
+                }
+            }
+
             mbar_wait(bar0 + s * 8, parity);
 
             // ---- pass 0: load (linear layout) -------------------------------------------------------
@@ -451,6 +504,10 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             if constexpr (FINE0) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) r[i] = pcx_mul(r[i], fine_phasor);
+            }
+            if constexpr (FINE == FINE_WALK) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = pcx_mul(r[i], __ldg(p.fine + fidx[i]));
             }
             if constexpr (DBG) {
                 if (p.dec && live) {
@@ -568,21 +625,48 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             }
             // reduce over the window's G threads
             constexpr int WIDTH = G < 32 ? G : 32;
+            if constexpr (G >= 32) {
+                // the window spans whole warps: REDUX.  bv is >= +0 and never NaN here, so the
+                // unsigned order of its bit pattern is the float order; among equal maxima the
+                // smallest index wins (the sequential scan's first-max rule)
+                const uint32_t bits = __float_as_uint(bv);
+                const uint32_t mx = __reduce_max_sync(0xffffffffu, bits);
+                bi = int(__reduce_min_sync(0xffffffffu, bits == mx ? uint32_t(bi) : 0xffffffffu));
+                bv = __uint_as_float(mx);
 #pragma unroll
-            for (int o = WIDTH / 2; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                argmax_merge(bv, bi, ov, oi);
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            } else {
+#pragma unroll
+                for (int o = WIDTH / 2; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    argmax_merge(bv, bi, ov, oi);
+                }
             }
             if constexpr (G > 32) {
-                // cross-warp: warp leaders publish, every thread folds the G/32 partials
+                // cross-warp: warp leaders publish one 16-byte partial {sum, value bits, index};
+                // lane l of every warp picks up partial l mod K and the K partials are folded with
+                // the same REDUX / xor-shuffle pattern (every aligned block of K lanes holds all K)
+                constexpr int K = G / 32;
                 const int wig = tg >> 5;
-                if (lane == 0) { red_sum[wig] = sum; red_val[wig] = bv; red_idx[wig] = bi; }
+                const uint32_t rbase = smem_u32(red_sum);
+                if (lane == 0)
+                    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(rbase + uint32_t(wig) * 16u),
+                                 "l"(__double_as_longlong(sum)),
+                                 "l"((unsigned long long)__float_as_uint(bv) | ((unsigned long long)uint32_t(bi) << 32))
+                                 : "memory");
                 group_sync<GROUP>(grp);
-                sum = red_sum[0]; bv = red_val[0]; bi = red_idx[0];
+                long long ps; unsigned long long pk;
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(ps), "=l"(pk)
+                             : "r"(rbase + uint32_t(lane & (K - 1)) * 16u));
+                sum = __longlong_as_double(ps);
+                const uint32_t bits = uint32_t(pk), idx = uint32_t(pk >> 32);
+                const uint32_t mx = __reduce_max_sync(0xffffffffu, bits);
+                bi = int(__reduce_min_sync(0xffffffffu, bits == mx ? idx : 0xffffffffu));
+                bv = __uint_as_float(mx);
 #pragma unroll
-                for (int q = 1; q < G / 32; ++q) { sum += red_sum[q]; argmax_merge(bv, bi, red_val[q], red_idx[q]); }
+                for (int o = K / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             }
             // neighbours of the peak, (bi-1) mod N and (bi+1) mod N, live in other threads' registers
             // (cyclic neighbours, LoRaDetector.hpp:56-57: N is a power of two, so the wrap is a mask)
@@ -619,7 +703,8 @@ inline bool fused_applicable(int sf, const DemodParams &p)
     if ((reinterpret_cast<uintptr_t>(p.iq) & 15u) != 0) return false; // TMA needs 16-byte aligned sources:
     if ((p.stride & 1ull) != 0 && p.n_windows > 1) return false;      // base aligned and an even sample stride
     if (p.n_windows >= (1ull << 31)) return false;
-    if (p.fine != nullptr && p.fine_step != 0.0f) return false;       // walking fine index: simple kernel
+    // walking fine index together with the fft/dec debug dumps: simple kernel
+    if (p.fine != nullptr && p.fine_step != 0.0f && (p.fft != nullptr || p.dec != nullptr)) return false;
     return true;
 }
 
@@ -638,13 +723,13 @@ inline void fill_pass0_tw(int sf, const float2 *tw_host, Pass0Tw &o)
         }
 }
 
-template <int SF, bool DBG, bool FINE0>
+template <int SF, bool DBG, int FINE>
 cudaError_t launch_fused_v(const DemodParams &p, const Pass0Tw &tw0, float2 phasor, cudaStream_t s, int sm_count)
 {
     using C = FusedCfg<SF>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(demod_fused_kernel<SF, DBG, FINE0>,
+        cudaError_t e = cudaFuncSetAttribute(demod_fused_kernel<SF, DBG, FINE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_done = true;
@@ -666,31 +751,33 @@ cudaError_t launch_fused_v(const DemodParams &p, const Pass0Tw &tw0, float2 phas
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, demod_fused_kernel<SF, DBG, FINE0>, p, tw0, phasor);
+    return cudaLaunchKernelEx(&cfg, demod_fused_kernel<SF, DBG, FINE>, p, tw0, phasor);
 }
 
 template <int SF>
-cudaError_t launch_fused_sf(const DemodParams &p, const Pass0Tw &tw0, bool fine0, float2 phasor,
+cudaError_t launch_fused_sf(const DemodParams &p, const Pass0Tw &tw0, int fine, float2 phasor,
                             cudaStream_t s, int sm_count)
 {
     const bool dbg = p.fft != nullptr || p.dec != nullptr;
-    if (dbg) return fine0 ? launch_fused_v<SF, true, true>(p, tw0, phasor, s, sm_count)
-                          : launch_fused_v<SF, true, false>(p, tw0, phasor, s, sm_count);
-    return fine0 ? launch_fused_v<SF, false, true>(p, tw0, phasor, s, sm_count)
-                 : launch_fused_v<SF, false, false>(p, tw0, phasor, s, sm_count);
+    if (fine == FINE_WALK) return dbg ? cudaErrorInvalidValue : launch_fused_v<SF, false, FINE_WALK>(p, tw0, phasor, s, sm_count);
+    if (dbg) return fine == FINE_CONST ? launch_fused_v<SF, true, FINE_CONST>(p, tw0, phasor, s, sm_count)
+                                       : launch_fused_v<SF, true, FINE_NONE>(p, tw0, phasor, s, sm_count);
+    return fine == FINE_CONST ? launch_fused_v<SF, false, FINE_CONST>(p, tw0, phasor, s, sm_count)
+                              : launch_fused_v<SF, false, FINE_NONE>(p, tw0, phasor, s, sm_count);
 }
 
-// fine0: multiply by the constant fine-tune phasor `phasor` (= fine[idx0], step == 0)
-inline cudaError_t launch_fused(int sf, const DemodParams &p, const Pass0Tw &tw0, bool fine0, float2 phasor,
+// fine: FINE_NONE, FINE_CONST (multiply by `phasor` = fine[idx0], step == 0) or FINE_WALK
+// (p.fine_x16 holds the index at every 16th sample)
+inline cudaError_t launch_fused(int sf, const DemodParams &p, const Pass0Tw &tw0, int fine, float2 phasor,
                                 cudaStream_t s, int sm_count)
 {
     switch (sf) {
-    case 7: return launch_fused_sf<7>(p, tw0, fine0, phasor, s, sm_count);
-    case 8: return launch_fused_sf<8>(p, tw0, fine0, phasor, s, sm_count);
-    case 9: return launch_fused_sf<9>(p, tw0, fine0, phasor, s, sm_count);
-    case 10: return launch_fused_sf<10>(p, tw0, fine0, phasor, s, sm_count);
-    case 11: return launch_fused_sf<11>(p, tw0, fine0, phasor, s, sm_count);
-    case 12: return launch_fused_sf<12>(p, tw0, fine0, phasor, s, sm_count);
+    case 7: return launch_fused_sf<7>(p, tw0, fine, phasor, s, sm_count);
+    case 8: return launch_fused_sf<8>(p, tw0, fine, phasor, s, sm_count);
+    case 9: return launch_fused_sf<9>(p, tw0, fine, phasor, s, sm_count);
+    case 10: return launch_fused_sf<10>(p, tw0, fine, phasor, s, sm_count);
+    case 11: return launch_fused_sf<11>(p, tw0, fine, phasor, s, sm_count);
+    case 12: return launch_fused_sf<12>(p, tw0, fine, phasor, s, sm_count);
     default: return cudaErrorInvalidValue;
     }
 }

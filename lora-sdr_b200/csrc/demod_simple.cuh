@@ -55,12 +55,12 @@ demod_simple_kernel(const DemodParams p)
         if (walk) {
             // sequential recurrence over the window (LoRaDemod.cpp:160-162)
             if (tid == 0) {
-                int idx = p.fine_idx0[w];
+                int idx = p.fine_x16[w * (N / 16)];
                 for (int i = 0; i < N; ++i) { fidx[i] = idx; idx = fine_next(idx, p.fine_step, p.fine_len); }
             }
             __syncthreads();
         }
-        const int idx_const = fine ? p.fine_idx0[w] : 0;
+        const int idx_const = p.fine_index0;
 
         // dechirp + digit-reversed load
         for (int j = tid; j < N; j += T) {

@@ -1,0 +1,65 @@
+// fine_prefix.cuh -- the fine-tune index (LoRaDemod.cpp:160-162) at every 16th dechirped
+// sample of a batch, computed on the device without walking the batch sequentially.
+//
+// The index is a one-word state x advanced once per sample by g(x) = wrap(trunc(fl32(
+// float(x) - d))) (common.cuh: fine_next, the literal recurrence).  The demod kernels need
+// the state at the start of every 16-sample chunk, X[q] = g^(16 q)(x0), q < W*N/16.
+// g is a map on the finite set [0, N*128), so powers of g are lookup tables and the
+// prefix is pointer jumping, radix R = 16:
+//
+//     T      = g^16                           one table entry = 16 literal steps
+//     P_0    = T,   P_(i+1) = P_i^R           (table composition, N*128 entries)
+//     X[m*b + r] = P_i^m [ X[r] ]             b = R^i, r < b, 1 <= m < R  (a chain of m lookups)
+//
+// ceil(log16(Q)) rounds of one small kernel each (5 for 2^19 chunks); everything is built
+// from fine_next, so the result is exact by construction (tests compare with the sequential
+// walk).  T only depends on (SF, d) and is cached in the context.
+#pragma once
+#include "common.cuh"
+
+namespace lorab200 {
+
+constexpr int kFineChunk = 16; // samples per prefix entry (= points per thread of the fused kernel)
+
+__global__ void fine_base_kernel(int32_t *__restrict__ T, float step, int len)
+{
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < len; x += gridDim.x * blockDim.x) {
+        int y = x;
+#pragma unroll
+        for (int i = 0; i < kFineChunk; ++i) y = fine_next(y, step, len);
+        T[x] = y;
+    }
+}
+
+constexpr int kFineRadix = 16;
+
+// One round with base b = R^i: thread r < b fills X[m*b + r], m = 1..R-1 (below q_end) by
+// walking P from X[r]; when `compose` is set every thread also writes Pn = P^R.  Round 0
+// (b == 1) stores X[0] = x0.
+__global__ void fine_round_kernel(const int32_t *__restrict__ P, int32_t *__restrict__ Pn,
+                                  int32_t *__restrict__ X, unsigned long long b,
+                                  unsigned long long q_end, int len, int x0, int compose)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+         i < b || (compose && i < (unsigned long long)len); i += stride) {
+        if (i < b) {
+            int x = (b == 1) ? x0 : X[i];
+            if (b == 1) X[0] = x0;
+            for (int m = 1; m < kFineRadix; ++m) {
+                const unsigned long long q = (unsigned long long)m * b + i;
+                if (q >= q_end) break;
+                x = P[x];
+                X[q] = x;
+            }
+        }
+        if (compose && i < (unsigned long long)len) {
+            int y = int(i);
+#pragma unroll
+            for (int m = 0; m < kFineRadix; ++m) y = P[y];
+            Pn[i] = y;
+        }
+    }
+}
+
+} // namespace lorab200

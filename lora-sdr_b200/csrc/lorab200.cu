@@ -23,6 +23,7 @@
 #include "demod_fused.cuh"
 #endif
 #include "fine_walk.h"
+#include "fine_prefix.cuh"
 #include "finalize.h"
 #include "tables.h"
 
@@ -128,11 +129,15 @@ struct lorab200_ctx {
 #endif
 
     // scratch for the host-buffer entry point and the fine-tune pre-roll
-    DevBuf d_iq, d_raw, d_fft, d_dec, d_idx0;
+    DevBuf d_iq, d_raw, d_fft, d_dec;
     void *h_raw = nullptr;   // pinned
     size_t h_raw_cap = 0;
-    void *h_idx0 = nullptr;  // pinned
-    size_t h_idx0_cap = 0;
+    // walking fine-tune index (fine_prefix.cuh): T = g^16 for the cached step, two ping-pong
+    // composition tables and the per-chunk states of the current batch
+    DevBuf d_fine_t, d_fine_p[2], d_fine_x;
+    bool fine_t_valid = false;
+    float fine_t_step = 0.0f;
+    cudaEvent_t fine_done = nullptr;          // last kernel that read the fine scratch
 };
 
 namespace {
@@ -217,17 +222,55 @@ cudaError_t launch_simple(int sf, const DemodParams &p, cudaStream_t s, int sm_c
     }
 }
 
-// Fine-tune index (LoRaDemod.cpp:160-162) at the start of every window, in closed form
-// (fine_walk.h): O(windows), not O(samples).
-void roll_fine(int32_t idx, float step, int32_t len, size_t n, size_t n_windows,
-               int32_t *idx0, int32_t *idx_end)
+bool stream_capturing(cudaStream_t s)
 {
-    const FineWalk walk(len, step);
-    for (size_t w = 0; w < n_windows; ++w) {
-        idx0[w] = idx;
-        if (step != 0.0f) idx = walk.advance(idx, n);
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return st != cudaStreamCaptureStatusNone;
+}
+
+// Walking fine-tune index (LoRaDemod.cpp:160-162): state at every 16th dechirped sample of
+// the batch, on the device, by pointer jumping (fine_prefix.cuh).  Enqueued on `s`.
+int fine_prefix(lorab200_ctx *c, int32_t x0, float step, int32_t len, size_t n_windows, cudaStream_t s)
+{
+    const unsigned long long q_end = (unsigned long long)n_windows * (c->n / kFineChunk);
+    int st;
+    if ((st = ensure_dev(c, c->d_fine_x, q_end * sizeof(int32_t)))) return st;
+    for (DevBuf *b : {&c->d_fine_t, &c->d_fine_p[0], &c->d_fine_p[1]})
+        if ((st = ensure_dev(c, *b, size_t(len) * sizeof(int32_t)))) return st;
+    // the scratch may still be in use by the previous call on another stream (not while `s` is
+    // being captured into a graph: a capture orders its own nodes)
+    if (!stream_capturing(s)) CU_TRY(c, cudaStreamWaitEvent(s, c->fine_done, 0));
+    const int threads = 256;
+    auto blocks = [&](unsigned long long n) {
+        unsigned long long b = (n + threads - 1) / threads;
+        const unsigned long long cap = (unsigned long long)c->sm_count * 16ull;
+        return unsigned(b < 1 ? 1 : (b > cap ? cap : b));
+    };
+    int32_t *T = static_cast<int32_t *>(c->d_fine_t.p);
+    const bool capturing = stream_capturing(s);
+    if (capturing || !c->fine_t_valid || c->fine_t_step != step) {
+        fine_base_kernel<<<blocks(len), threads, 0, s>>>(T, step, len);
+        CU_TRY(c, cudaGetLastError());
+        // a launch captured into a graph only runs at replay: do not let eager calls rely on it
+        c->fine_t_valid = !capturing;
+        c->fine_t_step = step;
+        c->launches++;
     }
-    *idx_end = idx;
+    const int32_t *P = T;
+    int32_t *X = static_cast<int32_t *>(c->d_fine_x.p);
+    int round = 0;
+    for (unsigned long long b = 1;; b *= kFineRadix, ++round) {
+        const int compose = (b * kFineRadix < q_end) ? 1 : 0; // the last round needs no further table
+        int32_t *Pn = static_cast<int32_t *>(c->d_fine_p[round & 1].p);
+        const unsigned long long work = (compose && (unsigned long long)len > b) ? (unsigned long long)len : b;
+        fine_round_kernel<<<blocks(work), threads, 0, s>>>(P, Pn, X, b, q_end, len, x0, compose);
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+        if (!compose) break;
+        P = Pn;
+    }
+    return LORAB200_OK;
 }
 
 // Common launch path. `results`/`raw` are device pointers (exactly one non-null).
@@ -267,37 +310,36 @@ int run_demod(lorab200_ctx *c, const void *iq_dev, size_t n_windows, size_t stri
         p.fine_step = fine->step;
     }
 
+    const bool walk = fine && fine->step != 0.0f;
+    if (fine && !walk) p.fine_index0 = fine->index;
+    if (walk) {
+        // per-chunk index states on the device; the end-of-batch index for the caller in closed
+        // form on the host (fine_walk.h), so this call stays asynchronous
+        int st = fine_prefix(c, fine->index, fine->step, p.fine_len, n_windows, s);
+        if (st) return st;
+        p.fine_x16 = static_cast<const int32_t *>(c->d_fine_x.p);
+        fine->index = FineWalk(p.fine_len, fine->step).advance(fine->index, uint64_t(n_windows) * c->n);
+    }
+
     cudaError_t e;
 #ifndef LORAB200_NO_FUSED
     if (!(c->flags & LORAB200_FLAG_SIMPLE_ONLY) && fused_applicable(c->sf, p)) {
         // fine-tune with a zero step: the index never moves (LoRaDemod.cpp:160 with
         // _finefreqError == 0), so the whole batch is multiplied by one phasor
         float2 phasor = make_float2(1.f, 0.f);
-        if (fine) {
+        if (fine && !walk) {
             const cfloat f = c->h_table[LORAB200_TABLE_FINE][size_t(fine->index)];
             phasor = make_float2(f.re, f.im);
         }
-        e = launch_fused(c->sf, p, c->tw0, fine != nullptr, phasor, s, c->sm_count);
+        e = launch_fused(c->sf, p, c->tw0, walk ? FINE_WALK : (fine ? FINE_CONST : FINE_NONE), phasor, s, c->sm_count);
         c->last_kernel = std::string("fused_sf") + std::to_string(c->sf);
     } else
 #endif
     {
-        if (fine) {
-            int st = ensure_pinned(c, c->h_idx0, c->h_idx0_cap, n_windows * sizeof(int32_t));
-            if (st) return st;
-            st = ensure_dev(c, c->d_idx0, n_windows * sizeof(int32_t));
-            if (st) return st;
-            int32_t end = fine->index;
-            roll_fine(fine->index, fine->step, p.fine_len, c->n, n_windows, static_cast<int32_t *>(c->h_idx0), &end);
-            CU_TRY(c, cudaMemcpyAsync(c->d_idx0.p, c->h_idx0, n_windows * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-            // h_idx0 is reused by the next call: make sure the copy has left the host buffer
-            CU_TRY(c, cudaStreamSynchronize(s));
-            fine->index = end;
-            p.fine_idx0 = static_cast<const int32_t *>(c->d_idx0.p);
-        }
         e = launch_simple(c->sf, p, s, c->sm_count);
         c->last_kernel = std::string("simple_sf") + std::to_string(c->sf);
     }
+    if (walk && e == cudaSuccess && !stream_capturing(s)) e = cudaEventRecord(c->fine_done, s);
     if (e != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "kernel launch", e);
     c->launches++;
     return LORAB200_OK;
@@ -356,6 +398,7 @@ int lorab200_create(lorab200_ctx **out, int device, int sf, uint32_t flags)
         if ((e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess) { st = fail(nullptr, LORAB200_ERR_CUDA, "cudaStreamCreate", e); break; }
         for (auto &ev : c->chunk_done)
             if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) break;
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fine_done, cudaEventDisableTiming);
         if (e != cudaSuccess) { st = fail(nullptr, LORAB200_ERR_CUDA, "cudaEventCreate", e); break; }
         build_dechirp_tables(sf, c->h_table[LORAB200_TABLE_UP], c->h_table[LORAB200_TABLE_DOWN]);
         build_fine_table(sf, c->h_table[LORAB200_TABLE_FINE]);
@@ -378,9 +421,9 @@ void lorab200_destroy(lorab200_ctx *c)
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     for (auto &ev : c->chunk_done) if (ev) cudaEventDestroy(ev);
     for (auto &t : c->d_table) if (t) cudaFree(t);
-    for (DevBuf *b : {&c->d_iq, &c->d_raw, &c->d_fft, &c->d_dec, &c->d_idx0}) if (b->p) cudaFree(b->p);
+    for (DevBuf *b : {&c->d_iq, &c->d_raw, &c->d_fft, &c->d_dec, &c->d_fine_t, &c->d_fine_p[0], &c->d_fine_p[1], &c->d_fine_x}) if (b->p) cudaFree(b->p);
+    if (c->fine_done) cudaEventDestroy(c->fine_done);
     if (c->h_raw) cudaFreeHost(c->h_raw);
-    if (c->h_idx0) cudaFreeHost(c->h_idx0);
     (void)cudaGetLastError();
     delete c;
 }
@@ -508,7 +551,7 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     if (cw * wbytes > (size_t(16) << 20)) cw = (size_t(16) << 20) / wbytes;
     if (cw == 0) cw = 1;
     if ((n_windows + cw - 1) / cw > 64) cw = (n_windows + 63) / 64;
-    // a walking fine-tune index is pre-rolled through per-context scratch: no pipelining
+    // a walking fine-tune index uses per-context scratch for its prefix (fine_prefix.cuh): one chunk
     if (fine && fine->step != 0.0f) cw = n_windows;
     const size_t n_chunks = (n_windows + cw - 1) / cw;
     const float2 *h_iq = reinterpret_cast<const float2 *>(iq);

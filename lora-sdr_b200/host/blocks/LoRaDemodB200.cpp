@@ -111,6 +111,7 @@ public:
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, setDebugPorts));
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, setMaxBatch));
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, getKernelLaunches));
+        this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, getDemodCalls));
         this->setupInput(0, typeid(std::complex<float>));
         this->setupOutput(0);
         this->setupOutput("raw", typeid(std::complex<float>));
@@ -154,6 +155,7 @@ public:
     void setDebugPorts(const bool enable) { _debugPorts = enable; }
     void setMaxBatch(const size_t n) { _maxBatch = std::max<size_t>(1, n); }
     unsigned long long getKernelLaunches(void) const { return lorab200_kernel_launches(_ctx); }
+    unsigned long long getDemodCalls(void) const { return _demodCalls; } // lorab200_demod_host calls so far
 
     void activate(void)
     {
@@ -442,6 +444,7 @@ private:
             lorab200_fine fine;
             fine.index = idxHere;
             fine.step = _finefreqError * _fineSteps;
+            ++_demodCalls;
             const int st = lorab200_demod_host(_ctx, reinterpret_cast<const float *>(in + at), count, N, _table, &fine,
                 c.res.data(), _debugPorts ? reinterpret_cast<float *>(c.fft.data()) : nullptr,
                 _debugPorts ? reinterpret_cast<float *>(c.dec.data()) : nullptr);
@@ -482,6 +485,7 @@ private:
     const int _sf;
     const size_t _fineSteps;
     lorab200_ctx *_ctx;
+    unsigned long long _demodCalls = 0;
     unsigned char _sync;
     float _thresh;
     size_t _mtu;

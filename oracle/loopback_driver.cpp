@@ -130,6 +130,7 @@ struct LoopOut
     float signal_power[64];
     int signal_error[64];
     char error[256];
+    unsigned long long calls;      /* lorab200_demod_host calls made by our demod */
 };
 
 /* Transmit side: packets -> encoder -> mod -> (+ noise) -> IQ samples (complex64) into iq_out. */
@@ -232,6 +233,7 @@ int loopback_rx(const LoopCfg *cfg, const float *iq, unsigned long long n_sample
         }
         out->dropped = decoder->call<unsigned long long>("getDropped");
         if (cfg->use_b200) out->launches = demod->call<unsigned long long>("getKernelLaunches");
+        if (cfg->use_b200) out->calls = demod->call<unsigned long long>("getDemodCalls");
         out->samples = demod->input("0")->totalElements();
         for (auto &l : demod->output("raw")->collectedLabels)
         {

@@ -153,6 +153,37 @@ def test_fine_tune_path(lib, oracle, cuda_ok, sf, step, flags):
     d.close()
 
 
+@pytest.mark.parametrize("step", [1.28, -3.7, 55.001, 0.4, 63.99, -64.0, 17.0, 3.001953125, -0.015625])
+@pytest.mark.parametrize("sf", [7, 8, 9, 10, 11, 12])
+def test_fused_kernel_walking_fine_index(lib, oracle, cuda_ok, sf, step):
+    """The steady-state data path of the reference (LoRaDemod.cpp:157-166 after sync: _finefreqError
+    != 0, the index walks once per sample) stays on the fused kernel: per-chunk index states from
+    the on-device pointer-jumping prefix, literal recurrence inside a chunk.  Batches end in a
+    partial tile; two consecutive calls continue the walk (state in/out)."""
+    n = 1 << sf
+    nw = {7: 1031, 8: 517, 9: 259, 10: 131, 11: 67, 12: 35}[sf]
+    iq, _ = synth_windows(sf, nw, seed=177 + sf, snr_db=-5.0)
+    d = lib.Demod(sf)
+    up, fine = d.table(lib.TABLE_UP), d.table(lib.TABLE_FINE)
+    idx0 = (n * 128 * 5) // 7
+    exp, end_exp, _, _ = oracle.demod_windows(sf, iq, nw, up, fine=fine, fine_idx=idx0, fine_step=step)
+    out, end, _, _ = d.demod_dev(_dev(iq), nw, fine=(idx0, step))
+    assert d.last_kernel.startswith("fused"), d.last_kernel
+    assert end == end_exp
+    _check_records(lib.results_to_numpy(out), exp, exact_power=False, sf=sf)
+    # split into two calls: the returned index feeds the second call
+    k = nw // 3
+    o1, mid, _, _ = d.demod_dev(_dev(iq[:k]), k, fine=(idx0, step))
+    o2, end2, _, _ = d.demod_dev(_dev(iq[k:]), nw - k, fine=(mid, step))
+    assert end2 == end_exp
+    got = np.concatenate([lib.results_to_numpy(o1), lib.results_to_numpy(o2)])
+    _check_records(got, exp, exact_power=False, sf=sf)
+    got_h, end_h, _, _ = d.demod_host(iq, nw, fine=(idx0, step))
+    assert end_h == end_exp
+    _check_records(got_h, exp, exact_power=True, sf=sf)
+    d.close()
+
+
 def test_detector_kat_through_gpu(lib, oracle, cuda_ok):
     """TestDetector.cpp:9-35 through the CUDA path: SF10, all 1024 symbols,
     genChirp down-chirp as the dechirp table, genChirp up-chirp(sym) as input:

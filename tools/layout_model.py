@@ -211,6 +211,62 @@ def check_banks(sf, accesses):
     return bad
 
 
+def fine_pad(j):
+    """FINE_WALK: word offset of fine-tune index j in a window's exchange area (demod_fused.cuh)"""
+    return j + 4 * (j >> 5)
+
+
+def check_fine_layout(sf):
+    """FINE_WALK index parking: thread t writes words fine_pad(16t + i) as four 128-bit stores and
+    reads its pass-0 samples' indices (32- or 64-bit loads).  Checks (1) the reader's address is
+    thread base + immediate, (2) write then read returns index j for sample j, (3) bank conflicts
+    (words, 32 banks; 128-bit: per quarter warp, 64-bit: per half warp, 32-bit: per warp)."""
+    c = cfg(sf)
+    n, g, wpt, e, r0 = c["n"], c["g"], c["wpt"], c["e"], c["r0"]
+    fstride = n + n // 8 + (16 if sf == 8 else 0)
+    assert fstride * 4 % 16 == 0
+    mem = {}
+    bad = []
+    lanes_of_warp = [(w, t) for w in range(wpt) for t in range(g)]
+    # writes
+    for q in range(4):
+        for w0 in range(0, len(lanes_of_warp), 32):
+            warp = lanes_of_warp[w0:w0 + 32]
+            addrs = []
+            for (w, t) in warp:
+                a = w * fstride + fine_pad(16 * t) + 4 * q
+                assert a % 4 == 0
+                for i in range(4):
+                    assert (w, a + i) not in mem
+                    mem[(w, a + i)] = 16 * t + 4 * q + i
+                addrs.append(a)
+            for h in range(0, len(warp), 8):
+                banks = [(a // 4) % 8 for a in addrs[h:h + 8]]
+                if max(banks.count(b) for b in set(banks)) > 1:
+                    bad.append(("fine write", q, w0 // 32, h))
+    # reads
+    width = 1 if e == 1 else 2
+    insts = [(0, cc) for cc in range(r0)] if e == 1 else [(eh, cc) for eh in range(e // 2) for cc in range(r0)]
+    for (eh, cc) in insts:
+        jc = eh * 2 * g + (n // r0) * cc
+        for w0 in range(0, len(lanes_of_warp), 32):
+            warp = lanes_of_warp[w0:w0 + 32]
+            addrs = []
+            for (w, t) in warp:
+                il = t if e == 1 else 2 * t
+                a = w * fstride + fine_pad(il) + fine_pad(jc)          # thread base + immediate
+                assert fine_pad(il) + fine_pad(jc) == fine_pad(il + jc), (sf, t, jc)
+                for i in range(width):
+                    assert mem[(w, a + i)] == il + jc + i
+                addrs.append(a)
+            per = 32 if width == 1 else 16
+            for h in range(0, len(warp), per):
+                banks = [(a // width) % (32 // width) for a in addrs[h:h + per]]
+                if max(banks.count(b) for b in set(banks)) > 1:
+                    bad.append(("fine read", eh, cc, w0 // 32, h))
+    return bad
+
+
 def main():
     rng = np.random.default_rng(0)
     ok = True
@@ -224,7 +280,7 @@ def main():
         got = model_window(sf, x, chirp, tw, acc)
         ref = np.fft.fft(x * chirp)
         err = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
-        bad = check_banks(sf, acc)
+        bad = check_banks(sf, acc) + check_fine_layout(sf)
         print(f"SF{sf}: b0={c['b0']} npass={c['npass']} G={c['g']} E={c['e']} fft err {err:.2e}  "
               f"exchange footprint/window {win_stride(c)} el  bank conflicts: {len(bad)}")
         for b in bad[:8]:
