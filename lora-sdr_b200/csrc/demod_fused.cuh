@@ -475,9 +475,18 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
                                    r[(2 * eh) * R0 + c], r[(2 * eh + 1) * R0 + c]);
                 }
             }
-            // the stage is now in registers: hand it back to the TMA for tile k + STAGES
-            group_sync<GROUP>(grp);
-            if (tg == 0 && k + STAGES < my_tiles) { fence_proxy_async(); issue(k + STAGES, s); }
+            // the stage is now in registers: hand it back to the TMA for tile k + STAGES.  Normally
+            // at once (one group barrier, then thread 0 issues the refill).  SF10 and SF12 instead
+            // issue the refill after the barrier that follows the exchange-0 scatter (every thread
+            // has read the stage by then), which saves one named barrier per tile: measured +2 % /
+            // +3 %; SF11 (one stage, two groups per CTA) loses 7 % to the later prefetch and keeps
+            // the early hand-back.  FINE_WALK keeps the early barrier: it also separates the index
+            // gather from the scatter.
+            constexpr bool LATE_REFILL = (SF == 10 || SF == 12) && FINE != FINE_WALK;
+            if constexpr (!LATE_REFILL) {
+                group_sync<GROUP>(grp);
+                if (tg == 0 && k + STAGES < my_tiles) { fence_proxy_async(); issue(k + STAGES, s); }
+            }
 
             // ---- dechirp ------------------------------------------------------------------------
             if constexpr (C::CHIRP_SMEM) {
@@ -553,13 +562,17 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
                 }
             }
 
-            // ---- exchange 0 (the previous tile's reads of X finished before the sync above) -----------
+            // ---- exchange 0.  The previous tile's reads of X are over: warp-sized groups passed the
+            // __syncwarp above, larger groups the cross-warp reduction barrier of the previous tile -----
 #pragma unroll
             for (int e = 0; e < E; ++e)
 #pragma unroll
                 for (int c = 0; c < R0; ++c)
                     sts64(sc0[e] + uint32_t(C::pad(slot_to_x<B0>(c))) * 8u, r[e * R0 + c]);
             group_sync<GROUP>(grp);
+            if constexpr (LATE_REFILL) {
+                if (tg == 0 && k + STAGES < my_tiles) { fence_proxy_async(); issue(k + STAGES, s); }
+            }
 #pragma unroll
             for (int y = 0; y < 16; ++y) r[y] = lds64(ga1 + uint32_t(C::pad(y << B0)) * 8u);
 
@@ -674,7 +687,9 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             const unsigned jr = (unsigned(bi) + 1u) & unsigned(N - 1);
             const int tl = int(jl & unsigned(G - 1)), yl = int(jl >> (SF - 4));
             const int tr = int(jr & unsigned(G - 1)), yr = int(jr >> (SF - 4));
-            const c64 nbv = pick16(r, tL == tl ? yl : yr);
+            // (only the warps that hold one of the two owner lanes run the select tree)
+            c64 nbv = r[0];
+            if (G <= 32 || __any_sync(0xffffffffu, tL == tl || tL == tr)) nbv = pick16(r, tL == tl ? yl : yr);
             // the record of this window is assembled in shared memory by the three lanes that
             // own its pieces; it is read back at the next flush (after a group-wide sync)
             if (live) {

@@ -544,10 +544,11 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     // Software pipeline over chunks of windows on two streams: the H2D copy of chunk
     // i+1 overlaps the kernel and the D2H copy of chunk i, and the host-side
     // finalisation (libm) of earlier chunks; at most 64 chunks.
-    // chunk = 2048 windows (the unit one thread finalises in ~0.1 ms), but between 2 and 16 MiB of IQ
+    // chunk = 8..16 MiB of IQ (measured on B200 / PCIe gen5, SF7 64 MiB batches: 2 MiB chunks
+    // 42 GB/s, 4 MiB 48, 8 MiB 49.4, 16 MiB 47.5 -- profiles/r01_e2e_chunk_sweep.txt)
     size_t cw = 2048;
     const size_t wbytes = n * sizeof(float2);
-    if (cw * wbytes < (size_t(2) << 20)) cw = (size_t(2) << 20) / wbytes;
+    if (cw * wbytes < (size_t(8) << 20)) cw = (size_t(8) << 20) / wbytes;
     if (cw * wbytes > (size_t(16) << 20)) cw = (size_t(16) << 20) / wbytes;
     if (cw == 0) cw = 1;
     if ((n_windows + cw - 1) / cw > 64) cw = (n_windows + 63) / 64;
@@ -586,21 +587,31 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     // soon as its results have landed, while later chunks are still in flight.  Large
     // batches split the chunks over a few threads so this stays hidden behind the H2D copy.
     std::atomic<int> ferr_code{int(cudaSuccess)};
-    const std::function<void(size_t)> finish = [&](size_t k) {
+    // finalisation tasks are slices of a chunk (<= ftask windows) so that the last chunk's tail is
+    // spread over the helper threads too
+    size_t ftask = 1024;
+    if (ftask > cw) ftask = cw;
+    const size_t per_chunk = (cw + ftask - 1) / ftask;
+    const std::function<void(size_t)> finish = [&](size_t task) {
+        const size_t k = task / per_chunk, sub = task % per_chunk;
+        const size_t c0 = k * cw, c1 = (c0 + cw < n_windows) ? c0 + cw : n_windows;
+        const size_t p0 = c0 + sub * ftask;
+        if (p0 >= c1) return;
+        const size_t p1 = (p0 + ftask < c1) ? p0 + ftask : c1;
         cudaError_t e = cudaEventSynchronize(c->chunk_done[k % 64]);
         if (e != cudaSuccess) { ferr_code = int(e); return; }
-        const size_t p0 = k * cw, p1 = (p0 + cw < n_windows) ? p0 + cw : n_windows;
         finalize_host(h_raw + p0, p1 - p0, c->pscale, out + p0);
     };
+    const size_t n_tasks = n_chunks * per_chunk;
     if (n_windows >= 16384 && n_chunks >= 4) {
         size_t n_thr = std::thread::hardware_concurrency() / 4;
         if (n_thr > 8) n_thr = 8;
-        if (n_thr > n_chunks) n_thr = n_chunks;
+        if (n_thr > n_tasks) n_thr = n_tasks;
         if (n_thr < 2) n_thr = 2;
         c->helpers.ensure(n_thr - 1);
-        c->helpers.parallel(n_chunks, finish);   // chunks are taken in order, so in completion order
+        c->helpers.parallel(n_tasks, finish);   // tasks are taken in order, so in completion order
     } else {
-        for (size_t k = 0; k < n_chunks; ++k) finish(k);
+        for (size_t k = 0; k < n_tasks; ++k) finish(k);
     }
     const cudaError_t ferr = cudaError_t(ferr_code.load());
     if (ferr != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "cudaEventSynchronize(chunk)", ferr);
