@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (0 = min(K, 100))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--simple", action="store_true", help="force the simple (non-fused) kernel")
+    ap.add_argument("--channels", type=int, default=1,
+                    help="BASELINE config 4 form: this many independent channel buffers of --windows windows each, "
+                         "demodulated by ONE lorab200_demod_multi_dev launch per step")
     ap.add_argument("--fine-step", type=float, default=None,
                     help="demodulate with a walking fine-tune index of this step per sample "
                          "(LoRaDemod.cpp:157-166 after sync); default: the detector-only form")
@@ -239,8 +242,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     m.build()
-    sf, nw, K, W = args.sf, args.windows, args.steps, args.warmup
+    sf, nw, K, W = args.sf, args.windows * args.channels, args.steps, args.warmup
     n = 1 << sf
+    nch, wpc = args.channels, args.windows
+    assert nch == 1 or args.fine_step is None, "--channels is the detector-only form"
     # the synthetic batches are resident and never rewritten: let consecutive launches overlap
     # their first loads with the previous launch's tail (LORAB200_FLAG_INPUT_STABLE)
     d = m.Demod(sf, device=local, flags=m.FLAG_SIMPLE_ONLY if args.simple else
@@ -264,25 +269,32 @@ def main():
         iq, s = synth_on_device(sf, nw, seed=0x10AA + 7919 * b + 104729 * rank, device=device)
         bufs.append(iq)
         syms.append(s)
+    fine = None if args.fine_step is None else (1234, float(args.fine_step))
+    # per-channel buffers (independent allocations) for the multi-channel form
+    segs = [[bufs[b][c * wpc:(c + 1) * wpc].clone() for c in range(nch)] for b in range(nbuf)] if nch > 1 else None
     out = torch.empty((nw, 4), dtype=torch.int32, device=device)
+
+    def launch(i, cuda_stream):
+        if nch > 1:
+            d.demod_multi_dev(segs[i % nbuf], wpc, out=out, stream=cuda_stream)
+        else:
+            d.demod_dev(bufs[i % nbuf], nw, out=out, stream=cuda_stream, fine=fine)
     torch.cuda.synchronize()
 
     # ---- correctness spot check on this rank (sampled windows vs the CPU oracle) -------------------
     parity = spot_check(m, d, sf, bufs[0], syms[0], out)
 
-    fine = None if args.fine_step is None else (1234, float(args.fine_step))
-
     # ---- device-resident timing: K steps in one CUDA graph ----------------------------------------------
     stream = torch.cuda.Stream(device=device)
     with torch.cuda.stream(stream):
         for i in range(max(3, W)):
-            d.demod_dev(bufs[i % nbuf], nw, out=out, stream=stream.cuda_stream, fine=fine)
+            launch(i, stream.cuda_stream)
         stream.synchronize()
         graph = torch.cuda.CUDAGraph()
         launches0 = d.kernel_launches
         with torch.cuda.graph(graph, stream=stream):
             for i in range(K):
-                d.demod_dev(bufs[i % nbuf], nw, out=out, stream=torch.cuda.current_stream().cuda_stream, fine=fine)
+                launch(i, torch.cuda.current_stream().cuda_stream)
         launches_per_graph = d.kernel_launches - launches0
         graph.replay()                       # warm replay (graph upload)
         stream.synchronize()
@@ -326,14 +338,22 @@ def main():
         pinned.append(pa)
         host_bufs.append(pa.array)
     host_out = np.empty(nw, m.RESULT_DTYPE)
+    def host_step(i):
+        hb = host_bufs[i % len(host_bufs)]
+        if nch > 1:   # the host-buffer entry point is per channel (one block per channel)
+            for c in range(nch):
+                d.demod_host(hb[c * wpc:(c + 1) * wpc], wpc, out=host_out[c * wpc:(c + 1) * wpc])
+        else:
+            d.demod_host(hb, nw, out=host_out)
+
     for i in range(3):
-        d.demod_host(host_bufs[i % len(host_bufs)], nw, out=host_out)
+        host_step(i)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(Ke):
-        d.demod_host(host_bufs[i % len(host_bufs)], nw, out=host_out)
+        host_step(i)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     te = torch.tensor([dt], device=device, dtype=torch.float64)
@@ -368,7 +388,9 @@ def main():
         "metric": METRIC, "value": value, "unit": "Msymbols/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(sf, nw), "sf": sf, "windows_per_step_per_gpu": nw,
+        "config": {"workload": workload_name(sf, nw) if nch == 1 else
+                   f"{nch} channels x SF={sf} x {wpc} windows per channel per GPU, one multi-channel launch per step",
+                   "sf": sf, "windows_per_step_per_gpu": nw, "channels_per_gpu": nch,
                    "l2": f"inputs rotate over {nbuf} distinct {step_bytes >> 20} MiB buffers "
                          f"({nbuf * step_bytes >> 20} MiB > 3x L2), so every step streams from HBM",
                    "timing": "K steps captured in one CUDA graph (programmatic dependent launch between steps, LORAB200_FLAG_INPUT_STABLE), CUDA events on the launching stream",

@@ -168,6 +168,27 @@ int lorab200_demod_dev(lorab200_ctx *ctx, const void *iq_dev, size_t n_windows,
                        void *cuda_stream);
 
 /*
+ * Multi-channel form: ONE launch over n_segments independent device buffers (the
+ * channels of a multi-channel receiver, BASELINE config 4: 256 channels x SF10), each
+ * holding windows_per_segment windows at stride_samples.  The reference would run one
+ * LoRaDemod block (one thread) per channel; here the channels share a launch so that
+ * small per-channel batches still fill the GPU.
+ *
+ *   iq_dev_list    HOST array of n_segments DEVICE pointers (complex64), n_segments
+ *                  <= LORAB200_MAX_SEGMENTS; the pointers travel as a kernel parameter,
+ *                  so the array may be reused as soon as the call returns
+ *   out_dev        device pointer, n_segments*windows_per_segment records; the
+ *                  record of window w of segment c is out_dev[c*windows_per_segment + w]
+ *
+ * Detector-only form (no fine-tune state, no debug dumps): per-channel fine-tune state
+ * belongs to per-channel calls of lorab200_demod_dev.  Asynchronous, like demod_dev.
+ */
+#define LORAB200_MAX_SEGMENTS 256
+int lorab200_demod_multi_dev(lorab200_ctx *ctx, const void *const *iq_dev_list, size_t n_segments,
+                             size_t windows_per_segment, size_t stride_samples, int table,
+                             lorab200_result *out_dev, void *cuda_stream);
+
+/*
  * Same, with HOST buffers: copies the IQ span to the device, launches, copies
  * results (and the optional fft/dec dumps) back, and synchronises.  This is
  * the call a Pothos::Block::work() makes with its port buffers.  Pinned

@@ -51,6 +51,7 @@ EXPORTS = [
     "lorab200_gen_chirp", "lorab200_demod_dev", "lorab200_demod_host", "lorab200_pack_symbols",
     "lorab200_kernel_launches", "lorab200_last_kernel", "lorab200_alloc_pinned",
     "lorab200_free_pinned", "lorab200_table_len", "lorab200_build_table", "lorab200_fine_advance",
+    "lorab200_demod_multi_dev",
 ]
 
 
@@ -139,6 +140,7 @@ def load_library() -> C.CDLL:
                                      C.POINTER(C.c_float)]
     L.lorab200_demod_dev.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp, vp, vp, vp]
     L.lorab200_demod_host.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp, vp, vp]
+    L.lorab200_demod_multi_dev.argtypes = [vp, C.POINTER(vp), sz, sz, sz, C.c_int, vp, vp]
     L.lorab200_pack_symbols.argtypes = [vp, sz, vp]
     L.lorab200_pack_symbols.restype = None
     L.lorab200_kernel_launches.argtypes = [vp]
@@ -288,6 +290,26 @@ class Demod:
             C.c_void_p(stream))
         self._check(st, "demod_dev")
         return out, (f.index if f is not None else None), fft, dec
+
+    def demod_multi_dev(self, segments, windows_per_segment: int, stride: int | None = None,
+                        table: int = TABLE_UP, out=None, stream=None):
+        """One launch over a list of CUDA tensors (one per channel), `windows_per_segment` windows each
+        (lorab200_demod_multi_dev).  Returns the result tensor [len(segments) * windows_per_segment, 4]."""
+        import torch
+
+        assert len(segments) > 0 and all(t.is_cuda and t.is_contiguous() for t in segments)
+        stride = self.n if stride is None else int(stride)
+        dev = segments[0].device
+        total = len(segments) * windows_per_segment
+        if out is None:
+            out = torch.empty((total, 4), dtype=torch.int32, device=dev)
+        ptrs = (C.c_void_p * len(segments))(*[t.data_ptr() for t in segments])
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        st = self.L.lorab200_demod_multi_dev(self.ctx, ptrs, len(segments), windows_per_segment, stride, table,
+                                             C.c_void_p(out.data_ptr()), C.c_void_p(stream))
+        self._check(st, "demod_multi_dev")
+        return out
 
     # ---- hot path, host buffers (what a Pothos work() calls) -----------------------
     def demod_host(self, iq, n_windows: int, stride: int | None = None, table: int = TABLE_UP,

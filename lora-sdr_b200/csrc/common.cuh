@@ -44,7 +44,17 @@ struct DemodParams {
     float2 *fft;              // optional [W][N]
     float2 *dec;              // optional [W][N]
     unsigned int early_iq;    // LORAB200_FLAG_INPUT_STABLE: IQ may be prefetched before the prior grid drains
+    unsigned int seg_windows; // multi-segment batches (lorab200_demod_multi_dev): windows per segment, else 0
 };
+
+// Multi-segment batches: the windows of a launch come from up to kMaxSegments independent
+// device buffers (one per channel of a multi-channel receiver), seg_windows windows each;
+// window w lives in segment w / seg_windows.  The base pointers travel as a kernel parameter
+// (constant bank): no staging copy, safe under CUDA-graph capture.
+constexpr int kMaxSegments = LORAB200_MAX_SEGMENTS;
+template <bool MULTI> struct SegList { };
+template <> struct SegList<true> { const float2 *p[kMaxSegments]; };
+
 
 // ---- exact complex arithmetic --------------------------------------------------
 __device__ __forceinline__ float2 cx_mul(float2 a, float2 b)

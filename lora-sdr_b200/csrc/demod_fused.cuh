@@ -255,9 +255,11 @@ enum { FINE_NONE = 0, FINE_CONST = 1, FINE_WALK = 2 };
 __host__ __device__ constexpr int fine_pad(int j) { return j + 4 * (j >> 5); }
 __device__ __forceinline__ int fine_pad_dyn(int j) { return j + 4 * (j >> 5); }
 
-template <int SF, bool DBG, int FINE>
+// MULTI: the batch is a list of segments (SegList, common.cuh); a tile never straddles two
+//        segments (the host requires seg_windows % WPT == 0)
+template <int SF, bool DBG, int FINE, bool MULTI = false>
 __global__ void __launch_bounds__(256, FusedCfg<SF>::CTAS_PER_SM)
-demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_phasor)
+demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_phasor, const SegList<MULTI> segs)
 {
     constexpr bool FINE0 = (FINE == FINE_CONST);
     using C = FusedCfg<SF>;
@@ -308,11 +310,18 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
         if (nw > WPT) nw = WPT;
         const uint32_t bytes = nw * N * 8u;
         mbar_expect_tx(bar0 + s * 8, bytes);
+        const float2 *src;
+        if constexpr (MULTI) {
+            const uint32_t c = w0 / p.seg_windows;
+            src = segs.p[c] + size_t(w0 - c * p.seg_windows) * p.stride;
+        } else {
+            src = p.iq + size_t(w0) * p.stride;
+        }
         if (WPT == 1 || p.stride == N) {
-            tma_load_1d(gbase + s * C::STAGE_BYTES, p.iq + size_t(w0) * p.stride, bytes, bar0 + s * 8);
+            tma_load_1d(gbase + s * C::STAGE_BYTES, src, bytes, bar0 + s * 8);
         } else {
             for (uint32_t i = 0; i < nw; ++i)
-                tma_load_1d(gbase + s * C::STAGE_BYTES + i * N * 8u, p.iq + size_t(w0 + i) * p.stride,
+                tma_load_1d(gbase + s * C::STAGE_BYTES + i * N * 8u, src + size_t(i) * p.stride,
                             N * 8u, bar0 + s * 8);
         }
     };
@@ -714,10 +723,16 @@ inline bool fused_applicable(int sf, const DemodParams &p)
 {
     if (sf < 7 || sf > 12) return false;
     const unsigned long long n = 1ull << sf;
-    (void)n;
+    // (multi-segment batches: the caller has checked every segment pointer, p.iq is the first)
     if ((reinterpret_cast<uintptr_t>(p.iq) & 15u) != 0) return false; // TMA needs 16-byte aligned sources:
     if ((p.stride & 1ull) != 0 && p.n_windows > 1) return false;      // base aligned and an even sample stride
     if (p.n_windows >= (1ull << 31)) return false;
+    if (p.seg_windows != 0) {
+        // multi-segment: tiles must not straddle segments; no debug dumps, no fine-tune
+        const unsigned wpt = n >= 512 ? 1u : unsigned(512 / n);
+        if (p.seg_windows % wpt != 0) return false;
+        if (p.fft != nullptr || p.dec != nullptr || p.fine != nullptr) return false;
+    }
     // walking fine index together with the fft/dec debug dumps: simple kernel
     if (p.fine != nullptr && p.fine_step != 0.0f && (p.fft != nullptr || p.dec != nullptr)) return false;
     return true;
@@ -738,13 +753,14 @@ inline void fill_pass0_tw(int sf, const float2 *tw_host, Pass0Tw &o)
         }
 }
 
-template <int SF, bool DBG, int FINE>
-cudaError_t launch_fused_v(const DemodParams &p, const Pass0Tw &tw0, float2 phasor, cudaStream_t s, int sm_count)
+template <int SF, bool DBG, int FINE, bool MULTI = false>
+cudaError_t launch_fused_v(const DemodParams &p, const Pass0Tw &tw0, float2 phasor, cudaStream_t s, int sm_count,
+                           const SegList<MULTI> &segs = SegList<MULTI>())
 {
     using C = FusedCfg<SF>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(demod_fused_kernel<SF, DBG, FINE>,
+        cudaError_t e = cudaFuncSetAttribute(demod_fused_kernel<SF, DBG, FINE, MULTI>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_done = true;
@@ -766,7 +782,7 @@ cudaError_t launch_fused_v(const DemodParams &p, const Pass0Tw &tw0, float2 phas
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, demod_fused_kernel<SF, DBG, FINE>, p, tw0, phasor);
+    return cudaLaunchKernelEx(&cfg, demod_fused_kernel<SF, DBG, FINE, MULTI>, p, tw0, phasor, segs);
 }
 
 template <int SF>
@@ -779,6 +795,22 @@ cudaError_t launch_fused_sf(const DemodParams &p, const Pass0Tw &tw0, int fine, 
                                        : launch_fused_v<SF, true, FINE_NONE>(p, tw0, phasor, s, sm_count);
     return fine == FINE_CONST ? launch_fused_v<SF, false, FINE_CONST>(p, tw0, phasor, s, sm_count)
                               : launch_fused_v<SF, false, FINE_NONE>(p, tw0, phasor, s, sm_count);
+}
+
+// multi-segment batch (detector-only form)
+inline cudaError_t launch_fused_multi(int sf, const DemodParams &p, const Pass0Tw &tw0, const SegList<true> &segs,
+                                      cudaStream_t s, int sm_count)
+{
+    const float2 one = make_float2(1.f, 0.f);
+    switch (sf) {
+    case 7: return launch_fused_v<7, false, FINE_NONE, true>(p, tw0, one, s, sm_count, segs);
+    case 8: return launch_fused_v<8, false, FINE_NONE, true>(p, tw0, one, s, sm_count, segs);
+    case 9: return launch_fused_v<9, false, FINE_NONE, true>(p, tw0, one, s, sm_count, segs);
+    case 10: return launch_fused_v<10, false, FINE_NONE, true>(p, tw0, one, s, sm_count, segs);
+    case 11: return launch_fused_v<11, false, FINE_NONE, true>(p, tw0, one, s, sm_count, segs);
+    case 12: return launch_fused_v<12, false, FINE_NONE, true>(p, tw0, one, s, sm_count, segs);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 // fine: FINE_NONE, FINE_CONST (multiply by `phasor` = fine[idx0], step == 0) or FINE_WALK

@@ -34,9 +34,9 @@ __device__ __forceinline__ int kiss_input_index(int j)
 
 constexpr int kSimpleThreads = 128;
 
-template <int SF>
+template <int SF, bool MULTI>
 __global__ void __launch_bounds__(kSimpleThreads)
-demod_simple_kernel(const DemodParams p)
+demod_simple_kernel(const DemodParams p, const SegList<MULTI> segs)
 {
     constexpr int N = 1 << SF;
     constexpr int T = kSimpleThreads;
@@ -49,7 +49,13 @@ demod_simple_kernel(const DemodParams p)
 
     const int tid = threadIdx.x;
     for (unsigned long long w = blockIdx.x; w < p.n_windows; w += gridDim.x) {
-        const float2 *in = p.iq + w * p.stride;
+        const float2 *in;
+        if constexpr (MULTI) {
+            const unsigned long long c = w / p.seg_windows;
+            in = segs.p[c] + (w - c * p.seg_windows) * p.stride;
+        } else {
+            in = p.iq + w * p.stride;
+        }
         const bool fine = p.fine != nullptr;
         const bool walk = fine && p.fine_step != 0.0f;
         if (walk) {

@@ -190,14 +190,15 @@ int upload_table(lorab200_ctx *c, int which)
     return LORAB200_OK;
 }
 
-template <int SF>
-cudaError_t launch_simple_sf(const DemodParams &p, cudaStream_t s, int sm_count)
+template <int SF, bool MULTI = false>
+cudaError_t launch_simple_sf(const DemodParams &p, cudaStream_t s, int sm_count,
+                             const SegList<MULTI> &segs = SegList<MULTI>())
 {
     constexpr int N = 1 << SF;
     const size_t smem = size_t(N) * sizeof(float2) + size_t(N) * sizeof(int);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(demod_simple_kernel<SF>,
+        cudaError_t e = cudaFuncSetAttribute(demod_simple_kernel<SF, MULTI>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
         attr_done = true;
@@ -205,7 +206,7 @@ cudaError_t launch_simple_sf(const DemodParams &p, cudaStream_t s, int sm_count)
     unsigned long long grid = p.n_windows;
     const unsigned long long cap = (unsigned long long)sm_count * 64ull;
     if (grid > cap) grid = cap; // grid-stride over windows
-    demod_simple_kernel<SF><<<unsigned(grid), kSimpleThreads, smem, s>>>(p);
+    demod_simple_kernel<SF, MULTI><<<unsigned(grid), kSimpleThreads, smem, s>>>(p, segs);
     return cudaGetLastError();
 }
 
@@ -227,6 +228,19 @@ bool stream_capturing(cudaStream_t s)
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { (void)cudaGetLastError(); return false; }
     return st != cudaStreamCaptureStatusNone;
+}
+
+cudaError_t launch_simple_multi(int sf, const DemodParams &p, const SegList<true> &segs, cudaStream_t s, int sm_count)
+{
+    switch (sf) {
+    case 7: return launch_simple_sf<7, true>(p, s, sm_count, segs);
+    case 8: return launch_simple_sf<8, true>(p, s, sm_count, segs);
+    case 9: return launch_simple_sf<9, true>(p, s, sm_count, segs);
+    case 10: return launch_simple_sf<10, true>(p, s, sm_count, segs);
+    case 11: return launch_simple_sf<11, true>(p, s, sm_count, segs);
+    case 12: return launch_simple_sf<12, true>(p, s, sm_count, segs);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 // Walking fine-tune index (LoRaDemod.cpp:160-162): state at every 16th dechirped sample of
@@ -520,6 +534,58 @@ int lorab200_demod_dev(lorab200_ctx *c, const void *iq_dev, size_t n_windows, si
     CU_TRY(c, cudaSetDevice(c->device));
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream); // NULL == CUDA default stream
     return run_demod(c, iq_dev, n_windows, stride_samples, table, fine, out_dev, nullptr, fft_dev, dec_dev, s);
+}
+
+int lorab200_demod_multi_dev(lorab200_ctx *c, const void *const *iq_dev_list, size_t n_segments,
+                             size_t windows_per_segment, size_t stride_samples, int table,
+                             lorab200_result *out_dev, void *cuda_stream)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    c->err.clear();
+    if (n_segments == 0 || windows_per_segment == 0) return LORAB200_OK;
+    if (!iq_dev_list || !out_dev) return fail(c, LORAB200_ERR_INVALID, "iq_dev_list / out_dev is null");
+    if (n_segments > size_t(kMaxSegments)) return fail(c, LORAB200_ERR_UNSUPPORTED, "more than LORAB200_MAX_SEGMENTS segments");
+    if (table != LORAB200_TABLE_UP && table != LORAB200_TABLE_DOWN)
+        return fail(c, LORAB200_ERR_INVALID, "table must be LORAB200_TABLE_UP or LORAB200_TABLE_DOWN");
+    if (windows_per_segment > 1 && stride_samples == 0) return fail(c, LORAB200_ERR_INVALID, "stride_samples must be > 0");
+    if (n_segments * windows_per_segment >= (size_t(1) << 31) || windows_per_segment >= (size_t(1) << 31))
+        return fail(c, LORAB200_ERR_UNSUPPORTED, "too many windows in one call");
+    CU_TRY(c, cudaSetDevice(c->device));
+    SegList<true> segs{};
+    bool aligned16 = true;
+    for (size_t i = 0; i < n_segments; ++i) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(iq_dev_list[i]);
+        if (a == 0) return fail(c, LORAB200_ERR_INVALID, "a segment pointer is null");
+        if (a & 7u) return fail(c, LORAB200_ERR_INVALID, "segment pointers must be 8-byte aligned");
+        if (a & 15u) aligned16 = false;
+        segs.p[i] = static_cast<const float2 *>(iq_dev_list[i]);
+    }
+    DemodParams p{};
+    p.iq = segs.p[0];
+    p.n_windows = n_segments * windows_per_segment;
+    p.stride = stride_samples;
+    p.chirp = c->d_table[table];
+    p.tw = c->d_table[LORAB200_TABLE_TWIDDLE];
+    p.power_scale = c->pscale;
+    p.out = out_dev;
+    p.fine_len = int(c->n * kFineSteps);
+    p.early_iq = (c->flags & LORAB200_FLAG_INPUT_STABLE) ? 1u : 0u;
+    p.seg_windows = unsigned(windows_per_segment);
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    cudaError_t e;
+#ifndef LORAB200_NO_FUSED
+    if (!(c->flags & LORAB200_FLAG_SIMPLE_ONLY) && aligned16 && fused_applicable(c->sf, p)) {
+        e = launch_fused_multi(c->sf, p, c->tw0, segs, s, c->sm_count);
+        c->last_kernel = std::string("fused_multi_sf") + std::to_string(c->sf);
+    } else
+#endif
+    {
+        e = launch_simple_multi(c->sf, p, segs, s, c->sm_count);
+        c->last_kernel = std::string("simple_multi_sf") + std::to_string(c->sf);
+    }
+    if (e != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "kernel launch", e);
+    c->launches++;
+    return LORAB200_OK;
 }
 
 int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size_t stride_samples,

@@ -184,6 +184,35 @@ def test_fused_kernel_walking_fine_index(lib, oracle, cuda_ok, sf, step):
     d.close()
 
 
+@pytest.mark.parametrize("sf,nseg,wps", [(7, 5, 12), (7, 3, 7), (8, 4, 6), (9, 6, 3), (10, 32, 8), (12, 3, 2)])
+def test_multi_segment_launch(lib, oracle, cuda_ok, sf, nseg, wps):
+    """lorab200_demod_multi_dev: one launch over independent per-channel device buffers; record
+    c*wps + w is window w of segment c.  (7, 3, 7): wps not a multiple of the SF7 tile -> simple kernel."""
+    import torch
+    n = 1 << sf
+    d = lib.Demod(sf)
+    up = d.table(lib.TABLE_UP)
+    segs, exps = [], []
+    for c in range(nseg):
+        iq, _ = synth_windows(sf, wps, seed=1000 * sf + c, snr_db=-3.0)
+        exps.append(oracle.demod_windows(sf, iq, wps, up)[0])
+        segs.append(torch.from_numpy(iq).cuda())
+    out = d.demod_multi_dev(segs, wps)
+    torch.cuda.synchronize()
+    tile = max(1, 512 // n)
+    assert d.last_kernel.startswith("fused_multi" if wps % tile == 0 else "simple_multi"), d.last_kernel
+    got = lib.results_to_numpy(out)
+    _check_records(got, np.concatenate(exps), exact_power=False, sf=sf)
+    # strided windows inside every segment (overlapping by half a window)
+    if wps > 1:
+        nw2 = 2 * wps - 1
+        exp2 = [oracle.demod_windows(sf, t.cpu().numpy().reshape(-1), nw2, up, stride=n // 2)[0] for t in segs]
+        out2 = d.demod_multi_dev(segs, nw2, stride=n // 2)
+        torch.cuda.synchronize()
+        _check_records(lib.results_to_numpy(out2), np.concatenate(exp2), exact_power=False, sf=sf)
+    d.close()
+
+
 def test_detector_kat_through_gpu(lib, oracle, cuda_ok):
     """TestDetector.cpp:9-35 through the CUDA path: SF10, all 1024 symbols,
     genChirp down-chirp as the dechirp table, genChirp up-chirp(sym) as input:
