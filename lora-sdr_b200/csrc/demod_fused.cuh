@@ -491,6 +491,8 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             // +3 %; SF11 (one stage, two groups per CTA) loses 7 % to the later prefetch and keeps
             // the early hand-back.  FINE_WALK keeps the early barrier: it also separates the index
             // gather from the scatter.
+            // (The fence.proxy.async before the refill stays: a build without it failed a parity
+            // test on the GPU and was not faster.)
             constexpr bool LATE_REFILL = (SF == 10 || SF == 12) && FINE != FINE_WALK;
             if constexpr (!LATE_REFILL) {
                 group_sync<GROUP>(grp);
