@@ -62,4 +62,69 @@ __global__ void fine_round_kernel(const int32_t *__restrict__ P, int32_t *__rest
     }
 }
 
+// ---- small batches: closed form per entry -----------------------------------------------
+// A block's work() calls with a handful of windows; building g^16 over the whole table is
+// then the dominant cost.  Instead every entry X[q] = g^(16 q)(x0) is evaluated independently
+// with the region walk of fine_walk.h (host: FineWalk::advance, tested exhaustively against
+// the sequential recurrence), restated for the device: a step is D+1 for 1 <= k < Kp, D for
+// k >= Kp (k = x - D), everything else falls back to the literal recurrence.  D, Kp and the
+// integer-step flag are computed once per call on the host (FineWalk's constructor).
+struct FineWalkDev {
+    int len;
+    float d;
+    int integer;
+    long long D, Kp;
+};
+
+__device__ __forceinline__ int fine_advance_dev(const FineWalkDev &fw, int x, unsigned long long n)
+{
+    const long long L = fw.len;
+    if (n == 0) return x;
+    if (fw.integer) {
+        long long m = ((long long)x - (long long)(n % (unsigned long long)L) * (fw.D % L)) % L;
+        if (m < 0) m += L;
+        return int(m);
+    }
+    const long long KP_NONE = 0x7fffffffffffffffll;
+    while (n > 0) {
+        const long long k = (long long)x - fw.D;
+        unsigned long long j = 0;
+        long long s = 0;
+        if (k >= 1) {
+            const bool r = (k >= fw.Kp);
+            s = fw.D + 1 - (r ? 1 : 0);
+            if (s == 0) return x;
+            if (s > 0) {
+                const long long lb = r ? fw.Kp : 1;
+                j = (unsigned long long)((k - lb) / s) + 1;
+            } else {
+                const long long a = -s;
+                long long room = (L - 1 - (long long)x) / a;
+                if (!r && fw.Kp != KP_NONE) {
+                    const long long q = (fw.Kp - 1 - k) / a + 1;
+                    if (q < room) room = q;
+                }
+                j = room > 0 ? (unsigned long long)room : 0;
+            }
+        }
+        if (j == 0) {
+            const int y = fine_next(x, fw.d, fw.len);
+            if (y == x) return x;
+            x = y;
+            --n;
+            continue;
+        }
+        if (j > n) j = n;
+        x = int((long long)x - (long long)j * s);
+        n -= j;
+    }
+    return x;
+}
+
+__global__ void fine_small_kernel(int32_t *__restrict__ X, const FineWalkDev fw, int x0, unsigned long long q_end)
+{
+    const unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < q_end) X[q] = fine_advance_dev(fw, x0, q * kFineChunk);
+}
+
 } // namespace lorab200

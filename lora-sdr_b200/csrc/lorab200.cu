@@ -107,6 +107,11 @@ private:
 };
 } // namespace
 
+constexpr unsigned long long kFineSmallEntries = 8192; // fine prefix: closed form per entry up to here
+constexpr size_t kRingSlots = 4, kRingSlotBytes = size_t(512) << 10; // pageable-input staging ring
+constexpr size_t kSmallBatchWindows = 16;          // lorab200_demod_host: zero-copy path up to here
+constexpr size_t kSmallBatchBytes = size_t(256) << 10;
+
 struct lorab200_ctx {
     Helpers helpers;
     int device = 0;
@@ -132,6 +137,13 @@ struct lorab200_ctx {
     DevBuf d_iq, d_raw, d_fft, d_dec;
     void *h_raw = nullptr;   // pinned
     size_t h_raw_cap = 0;
+    void *h_stage = nullptr; // pinned staging of small batches (read by the kernel over PCIe)
+    size_t h_stage_cap = 0;
+    // pageable callers (a framework's ordinary port buffers): large H2D copies are staged through
+    // a ring of pinned slots so that the PCIe copy of one slot overlaps the memcpy into the next
+    void *h_ring = nullptr;
+    cudaEvent_t ring_free[4] = {};
+    unsigned ring_next = 0;
     // walking fine-tune index (fine_prefix.cuh): T = g^16 for the cached step, two ping-pong
     // composition tables and the per-chunk states of the current batch
     DevBuf d_fine_t, d_fine_p[2], d_fine_x;
@@ -175,6 +187,38 @@ int ensure_pinned(lorab200_ctx *c, void *&p, size_t &cap, size_t bytes)
     cudaError_t e = cudaMallocHost(&p, want);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(c, LORAB200_ERR_NOMEM, "cudaMallocHost(scratch)", e); }
     cap = want;
+    return LORAB200_OK;
+}
+
+bool is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Host -> device copy of `bytes` on stream `s`.  Page-locked sources are copied directly;
+// pageable ones go through the context's ring of pinned slots (memcpy into a slot, async copy
+// out of it), which keeps the PCIe engine busy while the CPU fills the next slot.
+int h2d_copy(lorab200_ctx *c, void *dst, const void *src, size_t bytes, cudaStream_t s, bool pageable)
+{
+    if (!pageable) {
+        CU_TRY(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+        return LORAB200_OK;
+    }
+    if (!c->h_ring) {
+        cudaError_t e = cudaMallocHost(&c->h_ring, kRingSlots * kRingSlotBytes);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); c->h_ring = nullptr; return fail(c, LORAB200_ERR_NOMEM, "cudaMallocHost(ring)", e); }
+    }
+    for (size_t off = 0; off < bytes; off += kRingSlotBytes) {
+        const size_t len = bytes - off < kRingSlotBytes ? bytes - off : kRingSlotBytes;
+        const unsigned slot = c->ring_next++ % kRingSlots;
+        CU_TRY(c, cudaEventSynchronize(c->ring_free[slot])); // the copy that last used this slot is done
+        char *sp = static_cast<char *>(c->h_ring) + size_t(slot) * kRingSlotBytes;
+        std::memcpy(sp, static_cast<const char *>(src) + off, len);
+        CU_TRY(c, cudaMemcpyAsync(static_cast<char *>(dst) + off, sp, len, cudaMemcpyHostToDevice, s));
+        CU_TRY(c, cudaEventRecord(c->ring_free[slot], s));
+    }
     return LORAB200_OK;
 }
 
@@ -250,6 +294,17 @@ int fine_prefix(lorab200_ctx *c, int32_t x0, float step, int32_t len, size_t n_w
     const unsigned long long q_end = (unsigned long long)n_windows * (c->n / kFineChunk);
     int st;
     if ((st = ensure_dev(c, c->d_fine_x, q_end * sizeof(int32_t)))) return st;
+    if (q_end <= kFineSmallEntries) {
+        // small batch: every entry in closed form, one tiny launch, no tables
+        const FineWalk fw(len, step);
+        FineWalkDev dv;
+        dv.len = len; dv.d = step; dv.integer = fw.integer ? 1 : 0; dv.D = fw.D; dv.Kp = fw.Kp;
+        if (!stream_capturing(s)) CU_TRY(c, cudaStreamWaitEvent(s, c->fine_done, 0));
+        fine_small_kernel<<<unsigned((q_end + 127) / 128), 128, 0, s>>>(static_cast<int32_t *>(c->d_fine_x.p), dv, x0, q_end);
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+        return LORAB200_OK;
+    }
     for (DevBuf *b : {&c->d_fine_t, &c->d_fine_p[0], &c->d_fine_p[1]})
         if ((st = ensure_dev(c, *b, size_t(len) * sizeof(int32_t)))) return st;
     // the scratch may still be in use by the previous call on another stream (not while `s` is
@@ -413,6 +468,8 @@ int lorab200_create(lorab200_ctx **out, int device, int sf, uint32_t flags)
         for (auto &ev : c->chunk_done)
             if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) break;
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fine_done, cudaEventDisableTiming);
+        for (auto &ev : c->ring_free)
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
         if (e != cudaSuccess) { st = fail(nullptr, LORAB200_ERR_CUDA, "cudaEventCreate", e); break; }
         build_dechirp_tables(sf, c->h_table[LORAB200_TABLE_UP], c->h_table[LORAB200_TABLE_DOWN]);
         build_fine_table(sf, c->h_table[LORAB200_TABLE_FINE]);
@@ -438,6 +495,9 @@ void lorab200_destroy(lorab200_ctx *c)
     for (DevBuf *b : {&c->d_iq, &c->d_raw, &c->d_fft, &c->d_dec, &c->d_fine_t, &c->d_fine_p[0], &c->d_fine_p[1], &c->d_fine_x}) if (b->p) cudaFree(b->p);
     if (c->fine_done) cudaEventDestroy(c->fine_done);
     if (c->h_raw) cudaFreeHost(c->h_raw);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_ring) cudaFreeHost(c->h_ring);
+    for (auto &ev : c->ring_free) if (ev) cudaEventDestroy(ev);
     (void)cudaGetLastError();
     delete c;
 }
@@ -601,9 +661,27 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     const size_t span = (n_windows - 1) * stride_samples + n; // samples touched
     const size_t dump = n_windows * n * sizeof(float2);
     int st;
+    if ((st = ensure_pinned(c, c->h_raw, c->h_raw_cap, n_windows * sizeof(RawResult)))) return st;
+
+    // Small batches (a block's work() in the sequential phases of the receiver: one or two
+    // windows per call): latency, not bandwidth.  The span is staged in page-locked memory and
+    // the kernel reads it straight over PCIe and writes the raw records straight back (pinned
+    // memory is device-addressable under unified addressing): one launch and one stream
+    // synchronise instead of H2D copy + launch + D2H copy + event round trips.
+    if (!fft && !dec && n_windows <= kSmallBatchWindows && span * sizeof(float2) <= kSmallBatchBytes) {
+        if ((st = ensure_pinned(c, c->h_stage, c->h_stage_cap, span * sizeof(float2) + 16))) return st;
+        std::memcpy(c->h_stage, iq, span * sizeof(float2));
+        RawResultHost *h_raw = static_cast<RawResultHost *>(c->h_raw);
+        st = run_demod(c, c->h_stage, n_windows, stride_samples, table, fine, nullptr,
+                       reinterpret_cast<RawResult *>(h_raw), nullptr, nullptr, c->stream);
+        if (st) { cudaStreamSynchronize(c->stream); return st; }
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        finalize_host(h_raw, n_windows, c->pscale, out);
+        return LORAB200_OK;
+    }
+
     if ((st = ensure_dev(c, c->d_iq, span * sizeof(float2)))) return st;
     if ((st = ensure_dev(c, c->d_raw, n_windows * sizeof(RawResult)))) return st;
-    if ((st = ensure_pinned(c, c->h_raw, c->h_raw_cap, n_windows * sizeof(RawResult)))) return st;
     if (fft && (st = ensure_dev(c, c->d_fft, dump))) return st;
     if (dec && (st = ensure_dev(c, c->d_dec, dump))) return st;
 
@@ -625,6 +703,7 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     float2 *d_iq = static_cast<float2 *>(c->d_iq.p);
     RawResult *d_raw = static_cast<RawResult *>(c->d_raw.p);
     RawResultHost *h_raw = static_cast<RawResultHost *>(c->h_raw);
+    const bool pageable = is_pageable(iq);
     size_t copied_to = 0; // samples [0, copied_to) are already on the device
     for (size_t k = 0; k < n_chunks; ++k) {
         cudaStream_t s = (k & 1) ? c->stream2 : c->stream;
@@ -635,7 +714,10 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
             // stride < N: the head of this chunk was copied by chunk k-1 on the other
             // stream; order this stream after that chunk
             if (k > 0 && from > s0) CU_TRY(c, cudaStreamWaitEvent(s, c->chunk_done[(k - 1) % 64], 0));
-            CU_TRY(c, cudaMemcpyAsync(d_iq + from, h_iq + from, (s1 - from) * sizeof(float2), cudaMemcpyHostToDevice, s));
+            if ((st = h2d_copy(c, d_iq + from, h_iq + from, (s1 - from) * sizeof(float2), s, pageable))) {
+                cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2);
+                return st;
+            }
             copied_to = s1;
         }
         st = run_demod(c, d_iq + s0, nw, stride_samples, table, fine, nullptr, d_raw + w0,

@@ -112,6 +112,7 @@ public:
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, setMaxBatch));
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, getKernelLaunches));
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, getDemodCalls));
+        this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, getDemodWindows));
         this->setupInput(0, typeid(std::complex<float>));
         this->setupOutput(0);
         this->setupOutput("raw", typeid(std::complex<float>));
@@ -156,6 +157,7 @@ public:
     void setMaxBatch(const size_t n) { _maxBatch = std::max<size_t>(1, n); }
     unsigned long long getKernelLaunches(void) const { return lorab200_kernel_launches(_ctx); }
     unsigned long long getDemodCalls(void) const { return _demodCalls; } // lorab200_demod_host calls so far
+    unsigned long long getDemodWindows(void) const { return _demodWindows; } // windows submitted (incl. unused speculation)
 
     void activate(void)
     {
@@ -371,7 +373,7 @@ public:
     }
 
 private:
-    enum { kDebugWindows = 64 };
+    enum { kDebugWindows = 64, kIdleSpecMin = 16 };
 
     struct Window
     {
@@ -419,6 +421,16 @@ private:
             and (c.resetEach ? idxHere == 0 : this->cacheIdxAt((at - c.off)/N) == idxHere);
         if (not hit)
         {
+            //adapt the idle speculation depth to how much of the last idle batch was used: double
+            //after a batch that was consumed to the end, shrink to what was used otherwise, so
+            //that a long silence is demodulated in a few large calls while a busy channel does
+            //not pay for thousands of windows that the next preamble invalidates
+            if (c.count > 0 and c.resetEach and at >= c.off)
+            {
+                const size_t used = (at - c.off + N - 1)/N;
+                if (used >= c.count) _idleSpec = std::min(_idleSpec*2, _maxBatch);
+                else _idleSpec = std::max<size_t>(kIdleSpecMin, std::min(_idleSpec, 2*used));
+            }
             //how many windows may be demodulated speculatively from here?
             size_t count = 1;
             const size_t fit = (avail - at)/N;              //whole windows in the buffer from `at`
@@ -432,7 +444,7 @@ private:
                 }
                 else if (_state == STATE_FRAMESYNC and _finefreqError == 0.0f and idxHere == 0)
                 {
-                    count = maxWin;      //idle: every window starts from a reset fine tune state
+                    count = std::min(maxWin, _idleSpec);  //idle: every window starts from a reset fine tune state
                     resetEach = true;
                 }
             }
@@ -445,6 +457,7 @@ private:
             fine.index = idxHere;
             fine.step = _finefreqError * _fineSteps;
             ++_demodCalls;
+            _demodWindows += count;
             const int st = lorab200_demod_host(_ctx, reinterpret_cast<const float *>(in + at), count, N, _table, &fine,
                 c.res.data(), _debugPorts ? reinterpret_cast<float *>(c.fft.data()) : nullptr,
                 _debugPorts ? reinterpret_cast<float *>(c.dec.data()) : nullptr);
@@ -486,6 +499,8 @@ private:
     const size_t _fineSteps;
     lorab200_ctx *_ctx;
     unsigned long long _demodCalls = 0;
+    unsigned long long _demodWindows = 0;
+    size_t _idleSpec = kIdleSpecMin;        //current idle speculation depth (windows)
     unsigned char _sync;
     float _thresh;
     size_t _mtu;

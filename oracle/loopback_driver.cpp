@@ -31,6 +31,7 @@
 #include <Pothos/Framework.hpp>
 #include <cmath>
 #include <complex>
+#include <chrono>
 #include <cstring>
 #include <iostream>
 #include <sstream>
@@ -131,6 +132,9 @@ struct LoopOut
     int signal_error[64];
     char error[256];
     unsigned long long calls;      /* lorab200_demod_host calls made by our demod */
+    double seconds;                /* wall time of the feed/run loop (blocks already constructed) */
+    unsigned long long n_decoded;  /* decoded packets in total (lengths[] only keeps the first 64) */
+    unsigned long long windows;    /* windows submitted to the GPU by our demod (incl. unused speculation) */
 };
 
 /* Transmit side: packets -> encoder -> mod -> (+ noise) -> IQ samples (complex64) into iq_out. */
@@ -201,12 +205,16 @@ int loopback_rx(const LoopCfg *cfg, const float *iq, unsigned long long n_sample
         topology.commit();
         const cf *src = reinterpret_cast<const cf *>(iq);
         if (feed == 0) feed = n_samples;
+        const auto t_start = std::chrono::steady_clock::now();
         for (unsigned long long at = 0; at < n_samples; at += feed)
         {
             const unsigned long long n = std::min(feed, n_samples - at);
             ministream::Topology::feedStream(demod.get(), "0", src + at, n * sizeof(cf));
             topology.run();
         }
+
+        out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+        out->n_decoded = decoder->output("0")->collectedMessages.size();
 
         /* decoded packets */
         size_t bo = 0;
@@ -234,6 +242,7 @@ int loopback_rx(const LoopCfg *cfg, const float *iq, unsigned long long n_sample
         out->dropped = decoder->call<unsigned long long>("getDropped");
         if (cfg->use_b200) out->launches = demod->call<unsigned long long>("getKernelLaunches");
         if (cfg->use_b200) out->calls = demod->call<unsigned long long>("getDemodCalls");
+        if (cfg->use_b200) out->windows = demod->call<unsigned long long>("getDemodWindows");
         out->samples = demod->input("0")->totalElements();
         for (auto &l : demod->output("raw")->collectedLabels)
         {

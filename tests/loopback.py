@@ -20,7 +20,8 @@ class LoopOut(C.Structure):
                 ("dropped", C.c_ulonglong), ("launches", C.c_ulonglong), ("samples", C.c_ulonglong),
                 ("n_labels", C.c_int), ("labels", (C.c_char * 24) * 256), ("label_index", C.c_ulonglong * 256),
                 ("n_signals", C.c_int), ("signal_power", C.c_float * 64), ("signal_error", C.c_int * 64),
-                ("error", C.c_char * 256), ("calls", C.c_ulonglong)]
+                ("error", C.c_char * 256), ("calls", C.c_ulonglong),
+                ("seconds", C.c_double), ("n_decoded", C.c_ulonglong), ("windows", C.c_ulonglong)]
 
 
 def available():
@@ -72,7 +73,7 @@ def receive(sf, cr, iq, use_b200=False, debug_ports=True, mtu=512, sync=0x12, th
         syms.append(sarr[o:o + out.sym_lengths[i]].copy())
         o += out.sym_lengths[i]
     labels = [(out.labels[i].value.decode(), int(out.label_index[i])) for i in range(out.n_labels)]
-    return dict(decoded=dec, symbols=syms, dropped=int(out.dropped), launches=int(out.launches), calls=int(out.calls),
+    return dict(decoded=dec, symbols=syms, dropped=int(out.dropped), launches=int(out.launches), calls=int(out.calls), seconds=float(out.seconds), n_decoded=int(out.n_decoded), windows=int(out.windows),
                 samples=int(out.samples), labels=labels,
                 power=[float(out.signal_power[i]) for i in range(out.n_signals)],
                 error=[int(out.signal_error[i]) for i in range(out.n_signals)])

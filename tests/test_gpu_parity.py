@@ -213,6 +213,33 @@ def test_multi_segment_launch(lib, oracle, cuda_ok, sf, nseg, wps):
     d.close()
 
 
+@pytest.mark.parametrize("sf", [7, 8, 9, 10, 11, 12])
+def test_host_call_small_batches_zero_copy(lib, oracle, cuda_ok, sf):
+    """lorab200_demod_host with 1..16 windows (what a block's work() passes in the sequential
+    receiver phases) takes the staged zero-copy path: the records must be bit-identical to the
+    oracle's, dense and strided, with and without a walking fine-tune index, call after call."""
+    n = 1 << sf
+    d = lib.Demod(sf)
+    up, fine = d.table(lib.TABLE_UP), d.table(lib.TABLE_FINE)
+    iq, _ = synth_windows(sf, 24, seed=31 + sf, snr_db=-6.0)
+    flat = iq.reshape(-1)
+    for nw in (1, 2, 3, 7, 16):
+        if nw * n * 8 > 256 * 1024:
+            continue
+        exp = oracle.demod_windows(sf, flat, nw, up)[0]
+        got, _, _, _ = d.demod_host(flat[: nw * n], nw)
+        assert got.tobytes() == exp.tobytes(), f"dense nw={nw}"
+        if nw > 1:
+            stride = n // 2 + 2
+            exp = oracle.demod_windows(sf, flat, nw, up, stride=stride)[0]
+            got, _, _, _ = d.demod_host(flat, nw, stride=stride)
+            assert got.tobytes() == exp.tobytes(), f"strided nw={nw}"
+        exp, end_exp, _, _ = oracle.demod_windows(sf, flat, nw, up, fine=fine, fine_idx=77, fine_step=-9.25)
+        got, end, _, _ = d.demod_host(flat[: nw * n], nw, fine=(77, -9.25))
+        assert end == end_exp and got.tobytes() == exp.tobytes(), f"walking fine nw={nw}"
+    d.close()
+
+
 def test_detector_kat_through_gpu(lib, oracle, cuda_ok):
     """TestDetector.cpp:9-35 through the CUDA path: SF10, all 1024 symbols,
     genChirp down-chirp as the dechirp table, genChirp up-chirp(sym) as input:
