@@ -209,6 +209,32 @@ void lorab200_free_pinned(void *p);
  * per symbol (LoRaDemod.cpp:260,290: _outSymbols.as<int16_t*>()[n] = int16_t(value)). */
 void lorab200_pack_symbols(const lorab200_result *results, size_t n, int16_t *symbols);
 
+/* ---- modulator ----------------------------------- */
+
+/*
+ * Batched modulator: n_packets packets of syms_per_packet symbols each (uint16, DEVICE
+ * memory, as the reference encoder emits them) -> complex64 IQ in DEVICE memory, framed
+ * as LoRaMod.cpp:120-229 does: 10 preamble up-chirps, the two sync-word chirps, two
+ * down-chirps and a quarter down-chirp, the data symbols, `padding` symbols of zeros.
+ * Packet p occupies iq_dev[p * lorab200_mod_samples(...) ...].  Replaces /lora/lora_mod
+ * (LoRaMod.cpp:280-281; setSync, setPadding, setAmplitude, setOvs are the arguments).
+ *
+ *   mode  LORAB200_MOD_REFERENCE  genChirp's single-precision recurrences evaluated
+ *                                 literally (ChirpGenerator.hpp:22-47; one thread per packet):
+ *                                 sample phases bit-identical to the reference, samples
+ *                                 within 2 float ulp (polar() through double cos/sin);
+ *         LORAB200_MOD_IDEAL      closed-form chirps (ovs must be 1), every sample
+ *                                 independent, HBM write speed; differs from the reference
+ *                                 waveform by the reference's own accumulated rounding.
+ * Asynchronous on cuda_stream (NULL = CUDA's default stream).
+ */
+#define LORAB200_MOD_REFERENCE 0
+#define LORAB200_MOD_IDEAL 1
+size_t lorab200_mod_samples(int sf, int ovs, size_t syms_per_packet, size_t padding); /* samples per packet */
+int lorab200_mod_dev(lorab200_ctx *ctx, const uint16_t *symbols_dev, size_t n_packets,
+                     size_t syms_per_packet, unsigned sync, size_t padding, float ampl, int ovs,
+                     int mode, void *iq_dev, void *cuda_stream);
+
 /* ---- diagnostics ----------------------------------------------------------- */
 
 const char *lorab200_strerror(int status);

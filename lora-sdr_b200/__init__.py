@@ -30,6 +30,7 @@ STAMP_PATH = PKG_DIR / "liblorab200.so.stamp"
 
 TABLE_UP, TABLE_DOWN, TABLE_FINE, TABLE_TWIDDLE = 0, 1, 2, 3
 FLAG_DEFAULT, FLAG_SIMPLE_ONLY, FLAG_INPUT_STABLE = 0, 1, 2
+MOD_REFERENCE, MOD_IDEAL = 0, 1
 FINE_STEPS = 128
 
 RESULT_DTYPE = np.dtype(
@@ -51,7 +52,7 @@ EXPORTS = [
     "lorab200_gen_chirp", "lorab200_demod_dev", "lorab200_demod_host", "lorab200_pack_symbols",
     "lorab200_kernel_launches", "lorab200_last_kernel", "lorab200_alloc_pinned",
     "lorab200_free_pinned", "lorab200_table_len", "lorab200_build_table", "lorab200_fine_advance",
-    "lorab200_demod_multi_dev",
+    "lorab200_demod_multi_dev", "lorab200_mod_samples", "lorab200_mod_dev",
 ]
 
 
@@ -141,6 +142,9 @@ def load_library() -> C.CDLL:
     L.lorab200_demod_dev.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp, vp, vp, vp]
     L.lorab200_demod_host.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp, vp, vp]
     L.lorab200_demod_multi_dev.argtypes = [vp, C.POINTER(vp), sz, sz, sz, C.c_int, vp, vp]
+    L.lorab200_mod_samples.restype = sz
+    L.lorab200_mod_samples.argtypes = [C.c_int, C.c_int, sz, sz]
+    L.lorab200_mod_dev.argtypes = [vp, vp, sz, sz, C.c_uint, sz, C.c_float, C.c_int, C.c_int, vp, vp]
     L.lorab200_pack_symbols.argtypes = [vp, sz, vp]
     L.lorab200_pack_symbols.restype = None
     L.lorab200_kernel_launches.argtypes = [vp]
@@ -309,6 +313,24 @@ class Demod:
         st = self.L.lorab200_demod_multi_dev(self.ctx, ptrs, len(segments), windows_per_segment, stride, table,
                                              C.c_void_p(out.data_ptr()), C.c_void_p(stream))
         self._check(st, "demod_multi_dev")
+        return out
+
+    # ---- modulator (LoRaMod.cpp) ------------------------------------------------------------------
+    def mod_dev(self, symbols, sync: int = 0x12, padding: int = 1, ampl: float = 0.3, ovs: int = 1,
+                mode: int = 0, out=None, stream=None):
+        """symbols: CUDA int16/uint16 tensor [n_packets, syms_per_packet] -> complex64 [n_packets, samples]."""
+        import torch
+
+        assert symbols.is_cuda and symbols.is_contiguous() and symbols.dim() == 2 and symbols.element_size() == 2
+        npk, nsy = symbols.shape
+        spp = self.L.lorab200_mod_samples(self.sf, ovs, nsy, padding)
+        if out is None:
+            out = torch.empty((npk, spp), dtype=torch.complex64, device=symbols.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(symbols.device).cuda_stream
+        st = self.L.lorab200_mod_dev(self.ctx, C.c_void_p(symbols.data_ptr()), npk, nsy, sync, padding, ampl, ovs, mode,
+                                     C.c_void_p(out.data_ptr()), C.c_void_p(stream))
+        self._check(st, "mod_dev")
         return out
 
     # ---- hot path, host buffers (what a Pothos work() calls) -----------------------

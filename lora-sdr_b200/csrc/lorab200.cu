@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <atomic>
@@ -24,6 +25,7 @@
 #endif
 #include "fine_walk.h"
 #include "fine_prefix.cuh"
+#include "mod_synth.cuh"
 #include "finalize.h"
 #include "tables.h"
 
@@ -147,6 +149,7 @@ struct lorab200_ctx {
     // walking fine-tune index (fine_prefix.cuh): T = g^16 for the cached step, two ping-pong
     // composition tables and the per-chunk states of the current batch
     DevBuf d_fine_t, d_fine_p[2], d_fine_x;
+    DevBuf d_mod_phase, d_mod_phasor;         // modulator: REFERENCE-mode phases, IDEAL-mode exp(j*pi*m/N) table
     bool fine_t_valid = false;
     float fine_t_step = 0.0f;
     cudaEvent_t fine_done = nullptr;          // last kernel that read the fine scratch
@@ -492,7 +495,7 @@ void lorab200_destroy(lorab200_ctx *c)
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     for (auto &ev : c->chunk_done) if (ev) cudaEventDestroy(ev);
     for (auto &t : c->d_table) if (t) cudaFree(t);
-    for (DevBuf *b : {&c->d_iq, &c->d_raw, &c->d_fft, &c->d_dec, &c->d_fine_t, &c->d_fine_p[0], &c->d_fine_p[1], &c->d_fine_x}) if (b->p) cudaFree(b->p);
+    for (DevBuf *b : {&c->d_iq, &c->d_raw, &c->d_fft, &c->d_dec, &c->d_fine_t, &c->d_fine_p[0], &c->d_fine_p[1], &c->d_fine_x, &c->d_mod_phase, &c->d_mod_phasor}) if (b->p) cudaFree(b->p);
     if (c->fine_done) cudaEventDestroy(c->fine_done);
     if (c->h_raw) cudaFreeHost(c->h_raw);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -645,6 +648,75 @@ int lorab200_demod_multi_dev(lorab200_ctx *c, const void *const *iq_dev_list, si
     }
     if (e != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "kernel launch", e);
     c->launches++;
+    return LORAB200_OK;
+}
+
+size_t lorab200_mod_samples(int sf, int ovs, size_t syms_per_packet, size_t padding)
+{
+    if (sf < 7 || sf > 12 || ovs < 1 || ovs > 256) return 0;
+    return size_t(mod_samples_per_packet(1u << sf, unsigned(ovs), unsigned(syms_per_packet), unsigned(padding)));
+}
+
+int lorab200_mod_dev(lorab200_ctx *c, const uint16_t *symbols_dev, size_t n_packets, size_t syms_per_packet,
+                     unsigned sync, size_t padding, float ampl, int ovs, int mode, void *iq_dev, void *cuda_stream)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    c->err.clear();
+    if (n_packets == 0) return LORAB200_OK;
+    if (!iq_dev || (!symbols_dev && syms_per_packet)) return fail(c, LORAB200_ERR_INVALID, "symbols_dev / iq_dev is null");
+    if (ovs < 1 || ovs > 256) return fail(c, LORAB200_ERR_INVALID, "ovs must be in 1..256 (LoRaMod::setOvs)");
+    if (mode != LORAB200_MOD_REFERENCE && mode != LORAB200_MOD_IDEAL) return fail(c, LORAB200_ERR_INVALID, "unknown mode");
+    if (mode == LORAB200_MOD_IDEAL && ovs != 1) return fail(c, LORAB200_ERR_UNSUPPORTED, "LORAB200_MOD_IDEAL needs ovs == 1");
+    if (sync > 0xff) return fail(c, LORAB200_ERR_INVALID, "sync is one byte");
+    if (syms_per_packet >= (size_t(1) << 24) || padding >= (size_t(1) << 24))
+        return fail(c, LORAB200_ERR_UNSUPPORTED, "packet too long");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    ModParams p{};
+    p.symbols = symbols_dev;
+    p.n_packets = n_packets;
+    p.n_syms = unsigned(syms_per_packet);
+    p.padding = unsigned(padding);
+    p.sync = sync;
+    p.ovs = unsigned(ovs);
+    p.n = unsigned(c->n);
+    p.ampl = ampl;
+    p.samples_per_packet = mod_samples_per_packet(p.n, p.ovs, p.n_syms, p.padding);
+    p.out = static_cast<float2 *>(iq_dev);
+    const unsigned long long total = p.n_packets * p.samples_per_packet;
+    if (p.samples_per_packet >= (1ull << 32)) return fail(c, LORAB200_ERR_UNSUPPORTED, "packet too long");
+    int st;
+    auto blocks = [&](unsigned long long n) {
+        unsigned long long b = (n + 255) / 256;
+        const unsigned long long cap = (unsigned long long)c->sm_count * 16ull;
+        return unsigned(b < 1 ? 1 : (b > cap ? cap : b));
+    };
+    if (mode == LORAB200_MOD_IDEAL) {
+        if (!c->d_mod_phasor.p) {
+            // exp(j*pi*m/N), m < 2N: the 2N-point constellation every ideal chirp sample lies on
+            std::vector<float2> e(2 * c->n);
+            for (size_t m = 0; m < e.size(); ++m) {
+                const double a = M_PI * double(m) / double(c->n);
+                e[m] = make_float2(float(std::cos(a)), float(std::sin(a)));
+            }
+            if ((st = ensure_dev(c, c->d_mod_phasor, e.size() * sizeof(float2)))) return st;
+            CU_TRY(c, cudaMemcpy(c->d_mod_phasor.p, e.data(), e.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        }
+        p.phasor = static_cast<const float2 *>(c->d_mod_phasor.p);
+        mod_ideal_kernel<<<blocks(total), 256, 0, s>>>(p);
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+        c->last_kernel = "mod_ideal";
+        return LORAB200_OK;
+    }
+    if ((st = ensure_dev(c, c->d_mod_phase, total * sizeof(float)))) return st;
+    p.phase = static_cast<float *>(c->d_mod_phase.p);
+    mod_phase_kernel<<<unsigned((n_packets + 31) / 32), 32, 0, s>>>(p);
+    CU_TRY(c, cudaGetLastError());
+    mod_polar_kernel<<<blocks(total), 256, 0, s>>>(p);
+    CU_TRY(c, cudaGetLastError());
+    c->launches += 2;
+    c->last_kernel = "mod_reference";
     return LORAB200_OK;
 }
 

@@ -181,6 +181,75 @@ int loopback_tx(const LoopCfg *cfg, const unsigned char *payloads, const int *le
     }
 }
 
+/* Encoder only: payload bytes -> symbols (uint16) of one packet, by the reference LoRaEncoder. */
+int loopback_encode(const LoopCfg *cfg, const unsigned char *payload, int length,
+                    unsigned short *syms_out, int max_syms, int *n_syms, char *err256)
+{
+    try
+    {
+        static const char *crs[] = {"4/4", "4/5", "4/6", "4/7", "4/8"};
+        std::unique_ptr<Pothos::Block> encoder(Pothos::BlockRegistry::make("/lora/lora_encoder"));
+        encoder->call("setSpreadFactor", size_t(cfg->sf));
+        encoder->call("setCodingRate", std::string(crs[cfg->cr]));
+        ministream::Topology topology;
+        encoder->output("0")->collect = true;
+        topology.add(encoder.get());
+        topology.commit();
+        Pothos::Packet pkt;
+        pkt.payload = Pothos::BufferChunk(typeid(uint8_t), size_t(length));
+        std::memcpy(pkt.payload.as<void *>(), payload, size_t(length));
+        ministream::Topology::feedMessage(encoder.get(), "0", Pothos::Object(pkt));
+        topology.run();
+        const auto &msgs = encoder->output("0")->collectedMessages;
+        if (msgs.size() != 1) throw Pothos::Exception("loopback_encode", "encoder produced no packet");
+        const auto &out = msgs[0].extract<Pothos::Packet>();
+        const int n = int(out.payload.length / 2);
+        if (n > max_syms) throw Pothos::Exception("loopback_encode", "syms_out too small");
+        std::memcpy(syms_out, out.payload.as<const void *>(), size_t(n) * 2);
+        *n_syms = n;
+        return 0;
+    }
+    catch (const std::exception &ex)
+    {
+        std::strncpy(err256, ex.what(), 255);
+        return -1;
+    }
+}
+
+/* Modulator only: one packet of symbols -> IQ, by the reference LoRaMod (LoRaMod.cpp, ovs = 1). */
+int loopback_mod(const LoopCfg *cfg, const unsigned short *syms, int n_syms,
+                 float *iq_out, unsigned long long max_samples, unsigned long long *n_samples, char *err256)
+{
+    try
+    {
+        std::unique_ptr<Pothos::Block> mod(Pothos::BlockRegistry::make("/lora/lora_mod", size_t(cfg->sf)));
+        mod->call("setAmplitude", cfg->ampl);
+        mod->call("setPadding", size_t(cfg->padding));
+        mod->call("setSync", (unsigned char)(cfg->sync));
+        if (cfg->mtu > 0) mod->call("setOvs", size_t(cfg->mtu));   /* this entry point reads cfg->mtu as the oversampling */
+        ministream::Topology topology;
+        mod->output("0")->collect = true;
+        topology.add(mod.get());
+        topology.commit();
+        Pothos::Packet pkt;
+        pkt.payload = Pothos::BufferChunk(typeid(uint16_t), size_t(n_syms));
+        std::memcpy(pkt.payload.as<void *>(), syms, size_t(n_syms) * 2);
+        ministream::Topology::feedMessage(mod.get(), "0", Pothos::Object(pkt));
+        topology.run();
+        const auto &bytes = mod->output("0")->collectedBytes;
+        const unsigned long long n = bytes.size() / sizeof(cf);
+        if (n > max_samples) throw Pothos::Exception("loopback_mod", "iq_out too small");
+        std::memcpy(iq_out, bytes.data(), bytes.size());
+        *n_samples = n;
+        return 0;
+    }
+    catch (const std::exception &ex)
+    {
+        std::strncpy(err256, ex.what(), 255);
+        return -1;
+    }
+}
+
 /* Receive side: the SAME IQ samples -> DEMOD (reference or ours) -> decoder.
  * `feed` samples are appended to the demod's input per scheduler pass (0 = all at once). */
 int loopback_rx(const LoopCfg *cfg, const float *iq, unsigned long long n_samples, unsigned long long feed, LoopOut *out)

@@ -33,7 +33,38 @@ def _lib():
     L.loopback_tx.argtypes = [C.POINTER(LoopCfg), C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_void_p,
                               C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_char_p]
     L.loopback_rx.argtypes = [C.POINTER(LoopCfg), C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.POINTER(LoopOut)]
+    L.loopback_encode.argtypes = [C.POINTER(LoopCfg), C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                                  C.c_char_p]
+    L.loopback_mod.argtypes = [C.POINTER(LoopCfg), C.c_void_p, C.c_int, C.c_void_p, C.c_ulonglong,
+                               C.POINTER(C.c_ulonglong), C.c_char_p]
     return L
+
+
+def encode(sf, cr, payload):
+    """payload bytes -> symbols (uint16) of one packet, by the reference LoRaEncoder."""
+    L = _lib()
+    cfg = LoopCfg(sf, cr, 0, 0, 0, 0, 0x12, 1.0, 0.0, 0.0, 0)
+    syms = np.empty(4096, np.uint16)
+    n = C.c_int()
+    err = C.create_string_buffer(256)
+    if L.loopback_encode(C.byref(cfg), payload, len(payload), syms.ctypes.data_as(C.c_void_p), syms.size, C.byref(n), err):
+        raise RuntimeError(err.value.decode())
+    return syms[: n.value].copy()
+
+
+def modulate(sf, syms, padding=1, sync=0x12, ampl=1.0, ovs=1):
+    """one packet of symbols -> IQ (complex64), by the reference LoRaMod."""
+    L = _lib()
+    cfg = LoopCfg(sf, 0, 0, 0, padding, ovs, sync, ampl, 0.0, 0.0, 0)
+    syms = np.ascontiguousarray(syms, np.uint16)
+    cap = (16 + syms.size + padding) * (1 << sf) * ovs
+    iq = np.empty(cap, np.complex64)
+    n = C.c_ulonglong()
+    err = C.create_string_buffer(256)
+    if L.loopback_mod(C.byref(cfg), syms.ctypes.data_as(C.c_void_p), syms.size, iq.ctypes.data_as(C.c_void_p), cap,
+                      C.byref(n), err):
+        raise RuntimeError(err.value.decode())
+    return iq[: n.value].copy()
 
 
 def transmit(sf, cr, packets, padding=512, sync=0x12, ampl=1.0, sigma=0.0, seed=1):
