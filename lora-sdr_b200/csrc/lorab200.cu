@@ -703,7 +703,10 @@ int lorab200_mod_dev(lorab200_ctx *c, const uint16_t *symbols_dev, size_t n_pack
             CU_TRY(c, cudaMemcpy(c->d_mod_phasor.p, e.data(), e.size() * sizeof(float2), cudaMemcpyHostToDevice));
         }
         p.phasor = static_cast<const float2 *>(c->d_mod_phasor.p);
-        mod_ideal_kernel<<<blocks(total), 256, 0, s>>>(p);
+        const unsigned bpp = unsigned((p.samples_per_packet + kModIdealSpan - 1) / kModIdealSpan);
+        const unsigned long long nb = p.n_packets * bpp;
+        const unsigned long long cap = (unsigned long long)c->sm_count * 32ull;
+        mod_ideal_kernel<<<unsigned(nb < cap ? nb : cap), kModIdealSpan / 2, 0, s>>>(p, unsigned(c->sf), bpp);
         CU_TRY(c, cudaGetLastError());
         c->launches++;
         c->last_kernel = "mod_ideal";

@@ -115,7 +115,7 @@ __global__ void mod_polar_kernel(const ModParams p)
     }
 }
 
-// ---- IDEAL mode: closed form, two samples per thread ----------------------------------------
+// ---- IDEAL mode: closed form ---------------------------------------------------------------
 // phase index (units of pi/N) of sample i of a chirp with symbol s that starts at index M:
 //   up:   M + (i+1)(2s - N) + (i+1)(i+2)      down: M - ((i+1)(-N) + (i+1)(i+2))      (mod 2N)
 // a full chirp advances the index by N (mod 2N) whatever its symbol.
@@ -128,41 +128,46 @@ __device__ __forceinline__ unsigned mod_ideal_index(unsigned N, unsigned M, unsi
     return (M + inc) & m2;
 }
 
-__global__ void mod_ideal_kernel(const ModParams p)
+// One block = 512 consecutive samples of one packet (two per thread, one 16-byte store each);
+// the only division is the block -> packet split, N is a power of two.
+constexpr int kModIdealSpan = 512;
+
+__device__ __forceinline__ float2 mod_ideal_sample(const ModParams &p, unsigned long long pk, unsigned at,
+                                                   unsigned sf, unsigned head, unsigned Mq, unsigned sw0, unsigned sw1)
 {
     const unsigned N = p.n;
-    const unsigned long long spp = p.samples_per_packet;
-    const unsigned long long total = p.n_packets * spp;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned m;
+    if (at < head) {
+        const unsigned c = at >> sf, i = at & (N - 1);
+        const bool down = c >= kModPreamble + 2;
+        const unsigned s = c == kModPreamble ? sw0 : (c == kModPreamble + 1 ? sw1 : 0u);
+        m = mod_ideal_index(N, (c & 1u) * N, s, i, down);
+    } else if (at < head + N / 4) {
+        m = mod_ideal_index(N, 0, 0, at - head, true);           // 14 full chirps: back at index 0
+    } else {
+        const unsigned d = at - head - N / 4;
+        const unsigned k = d >> sf, i = d & (N - 1);
+        if (k >= p.n_syms) return make_float2(0.0f, 0.0f);        // padding (LoRaMod.cpp:224)
+        m = mod_ideal_index(N, Mq + (k & 1u) * N, p.symbols[pk * p.n_syms + k], i, false);
+    }
+    const float2 e = __ldg(p.phasor + m);
+    return make_float2(__fmul_rn(p.ampl, e.x), __fmul_rn(p.ampl, e.y));
+}
+
+__global__ void __launch_bounds__(kModIdealSpan / 2) mod_ideal_kernel(const ModParams p, unsigned sf, unsigned blocks_per_packet)
+{
+    const unsigned N = p.n;
     const unsigned head = kModHeadChirps * N;            // samples before the quarter chirp
-    // index after the quarter chirp (N/4 samples of a down-chirp from M = 0)
-    const unsigned Mq = mod_ideal_index(N, 0, 0, N / 4 - 1, true);
+    const unsigned Mq = mod_ideal_index(N, 0, 0, N / 4 - 1, true); // index after the quarter chirp
     const unsigned sw0 = (p.sync >> 4) * 8, sw1 = (p.sync & 0xf) * 8;
-    for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
-        const unsigned long long pk = g / spp;
-        const unsigned at = unsigned(g - pk * spp);
-        float2 v = make_float2(0.0f, 0.0f);
-        unsigned m = 0;
-        bool live = true;
-        if (at < head) {
-            const unsigned c = at / N, i = at % N;
-            const bool down = c >= kModPreamble + 2;
-            const unsigned s = c == kModPreamble ? sw0 : (c == kModPreamble + 1 ? sw1 : 0u);
-            m = mod_ideal_index(N, (c & 1u) * N, s, i, down);
-        } else if (at < head + N / 4) {
-            m = mod_ideal_index(N, 0, 0, at - head, true);       // 14 full chirps: back at index 0
-        } else {
-            const unsigned d = at - head - N / 4;
-            const unsigned k = d / N, i = d % N;
-            if (k < p.n_syms) m = mod_ideal_index(N, Mq + (k & 1u) * N, p.symbols[pk * p.n_syms + k], i, false);
-            else live = false;                                    // padding
-        }
-        if (live) {
-            const float2 e = __ldg(p.phasor + m);
-            v.x = __fmul_rn(p.ampl, e.x);
-            v.y = __fmul_rn(p.ampl, e.y);
-        }
-        p.out[g] = v;
+    const unsigned long long n_blocks = p.n_packets * blocks_per_packet;
+    for (unsigned long long b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const unsigned long long pk = b / blocks_per_packet;
+        const unsigned at = unsigned(b - pk * blocks_per_packet) * kModIdealSpan + 2 * threadIdx.x;
+        if (at >= p.samples_per_packet) continue;        // samples_per_packet is a multiple of 32
+        const float2 a = mod_ideal_sample(p, pk, at, sf, head, Mq, sw0, sw1);
+        const float2 c = mod_ideal_sample(p, pk, at + 1, sf, head, Mq, sw0, sw1);
+        *reinterpret_cast<float4 *>(p.out + pk * p.samples_per_packet + at) = make_float4(a.x, a.y, c.x, c.y);
     }
 }
 
