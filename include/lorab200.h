@@ -235,6 +235,37 @@ int lorab200_mod_dev(lorab200_ctx *ctx, const uint16_t *symbols_dev, size_t n_pa
                      size_t syms_per_packet, unsigned sync, size_t padding, float ampl, int ovs,
                      int mode, void *iq_dev, void *cuda_stream);
 
+/* ---- decoder ------------------------------------- */
+
+/* The setters of /lora/lora_decoder (LoRaDecoder.cpp:137-183); interleaving is always on (the
+ * reference's non-interleaved branch only forwards the symbols), the whitening switch is
+ * not consulted by the reference decoder either. */
+typedef struct lorab200_decoder_cfg {
+    int32_t ppm;              /* setSymbolSize, 0 = SF (must be 0 or 5..SF) */
+    int32_t rdd;              /* setCodingRate "4/4".."4/8" -> 0..4 */
+    int32_t explicit_header;  /* enableExplicit */
+    int32_t hdr;              /* enableHdr */
+    int32_t data_length;      /* setDataLength (implicit mode) */
+    int32_t crcc;             /* enableCrcc */
+    int32_t error_check;      /* enableErrorCheck */
+} lorab200_decoder_cfg;
+
+#define LORAB200_DECODE_DROPPED (-1) /* LoRaDecoder::drop() */
+#define LORAB200_DECODE_IGNORED (-2) /* fewer than 8 symbols: no output, no drop (LoRaDecoder.cpp:208) */
+#define LORAB200_DECODE_NO_ROOM (-3) /* bytes_stride too small for this packet */
+
+/*
+ * Batched decoder: n_packets demodulated symbol packets (DEVICE memory, packet p at
+ * symbols_dev + p*symbols_stride, n_symbols_dev[p] valid symbols or symbols_stride each when
+ * n_symbols_dev is NULL) -> payload bytes (packet p at bytes_dev + p*bytes_stride) and
+ * lengths_dev[p] (>= 0, or one of the codes above).  Replaces LoRaDecoder::work()
+ * (LoRaDecoder.cpp:196-397), bit-exactly, one packet per thread.  Asynchronous on cuda_stream.
+ */
+int lorab200_decode_dev(lorab200_ctx *ctx, const uint16_t *symbols_dev, size_t n_packets,
+                        size_t symbols_stride, const int32_t *n_symbols_dev,
+                        const lorab200_decoder_cfg *cfg, uint8_t *bytes_dev, size_t bytes_stride,
+                        int32_t *lengths_dev, void *cuda_stream);
+
 /* ---- diagnostics ----------------------------------------------------------- */
 
 const char *lorab200_strerror(int status);

@@ -52,7 +52,7 @@ EXPORTS = [
     "lorab200_gen_chirp", "lorab200_demod_dev", "lorab200_demod_host", "lorab200_pack_symbols",
     "lorab200_kernel_launches", "lorab200_last_kernel", "lorab200_alloc_pinned",
     "lorab200_free_pinned", "lorab200_table_len", "lorab200_build_table", "lorab200_fine_advance",
-    "lorab200_demod_multi_dev", "lorab200_mod_samples", "lorab200_mod_dev",
+    "lorab200_demod_multi_dev", "lorab200_mod_samples", "lorab200_mod_dev", "lorab200_decode_dev",
 ]
 
 
@@ -142,6 +142,7 @@ def load_library() -> C.CDLL:
     L.lorab200_demod_dev.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp, vp, vp, vp]
     L.lorab200_demod_host.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp, vp, vp]
     L.lorab200_demod_multi_dev.argtypes = [vp, C.POINTER(vp), sz, sz, sz, C.c_int, vp, vp]
+    L.lorab200_decode_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, vp, vp]
     L.lorab200_mod_samples.restype = sz
     L.lorab200_mod_samples.argtypes = [C.c_int, C.c_int, sz, sz]
     L.lorab200_mod_dev.argtypes = [vp, vp, sz, sz, C.c_uint, sz, C.c_float, C.c_int, C.c_int, vp, vp]
@@ -314,6 +315,27 @@ class Demod:
                                              C.c_void_p(out.data_ptr()), C.c_void_p(stream))
         self._check(st, "demod_multi_dev")
         return out
+
+    # ---- decoder (LoRaDecoder.cpp) ----------------------------------------------------------------
+    def decode_dev(self, symbols, n_symbols=None, ppm=0, rdd=4, explicit_header=True, hdr=False, data_length=8,
+                   crcc=False, error_check=False, bytes_stride=264, stream=None):
+        """symbols: CUDA int16/uint16 tensor [n_packets, stride]; n_symbols: optional CUDA int32 [n_packets].
+        Returns (bytes uint8 [n_packets, bytes_stride], lengths int32 [n_packets])."""
+        import torch
+
+        assert symbols.is_cuda and symbols.is_contiguous() and symbols.dim() == 2 and symbols.element_size() == 2
+        npk, stride = symbols.shape
+        cfg = (C.c_int32 * 7)(ppm, rdd, int(explicit_header), int(hdr), data_length, int(crcc), int(error_check))
+        out = torch.zeros((npk, bytes_stride), dtype=torch.uint8, device=symbols.device)
+        lengths = torch.empty(npk, dtype=torch.int32, device=symbols.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(symbols.device).cuda_stream
+        st = self.L.lorab200_decode_dev(self.ctx, C.c_void_p(symbols.data_ptr()), npk, stride,
+                                        C.c_void_p(n_symbols.data_ptr()) if n_symbols is not None else None,
+                                        C.cast(cfg, C.c_void_p), C.c_void_p(out.data_ptr()), bytes_stride,
+                                        C.c_void_p(lengths.data_ptr()), C.c_void_p(stream))
+        self._check(st, "decode_dev")
+        return out, lengths
 
     # ---- modulator (LoRaMod.cpp) ------------------------------------------------------------------
     def mod_dev(self, symbols, sync: int = 0x12, padding: int = 1, ampl: float = 0.3, ovs: int = 1,

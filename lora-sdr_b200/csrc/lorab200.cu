@@ -26,6 +26,7 @@
 #include "fine_walk.h"
 #include "fine_prefix.cuh"
 #include "mod_synth.cuh"
+#include "decode.cuh"
 #include "finalize.h"
 #include "tables.h"
 
@@ -149,6 +150,7 @@ struct lorab200_ctx {
     // walking fine-tune index (fine_prefix.cuh): T = g^16 for the cached step, two ping-pong
     // composition tables and the per-chunk states of the current batch
     DevBuf d_fine_t, d_fine_p[2], d_fine_x;
+    DevBuf d_dec_scratch;                     // decoder: per-packet symbol / codeword / byte scratch
     DevBuf d_mod_phase, d_mod_phasor;         // modulator: REFERENCE-mode phases, IDEAL-mode exp(j*pi*m/N) table
     bool fine_t_valid = false;
     float fine_t_step = 0.0f;
@@ -495,7 +497,7 @@ void lorab200_destroy(lorab200_ctx *c)
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     for (auto &ev : c->chunk_done) if (ev) cudaEventDestroy(ev);
     for (auto &t : c->d_table) if (t) cudaFree(t);
-    for (DevBuf *b : {&c->d_iq, &c->d_raw, &c->d_fft, &c->d_dec, &c->d_fine_t, &c->d_fine_p[0], &c->d_fine_p[1], &c->d_fine_x, &c->d_mod_phase, &c->d_mod_phasor}) if (b->p) cudaFree(b->p);
+    for (DevBuf *b : {&c->d_iq, &c->d_raw, &c->d_fft, &c->d_dec, &c->d_fine_t, &c->d_fine_p[0], &c->d_fine_p[1], &c->d_fine_x, &c->d_mod_phase, &c->d_mod_phasor, &c->d_dec_scratch}) if (b->p) cudaFree(b->p);
     if (c->fine_done) cudaEventDestroy(c->fine_done);
     if (c->h_raw) cudaFreeHost(c->h_raw);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -648,6 +650,50 @@ int lorab200_demod_multi_dev(lorab200_ctx *c, const void *const *iq_dev_list, si
     }
     if (e != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "kernel launch", e);
     c->launches++;
+    return LORAB200_OK;
+}
+
+int lorab200_decode_dev(lorab200_ctx *c, const uint16_t *symbols_dev, size_t n_packets, size_t symbols_stride,
+                        const int32_t *n_symbols_dev, const lorab200_decoder_cfg *cfg, uint8_t *bytes_dev,
+                        size_t bytes_stride, int32_t *lengths_dev, void *cuda_stream)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    c->err.clear();
+    if (n_packets == 0) return LORAB200_OK;
+    if (!symbols_dev || !cfg || !bytes_dev || !lengths_dev) return fail(c, LORAB200_ERR_INVALID, "null pointer");
+    if (cfg->rdd < 0 || cfg->rdd > 4) return fail(c, LORAB200_ERR_INVALID, "rdd must be 0..4");
+    const int ppm = cfg->ppm ? cfg->ppm : c->sf;
+    if (ppm < 5 || ppm > c->sf) return fail(c, LORAB200_ERR_INVALID, "ppm must be 0 or 5..SF (LoRaDecoder.cpp:202-203)");
+    if (cfg->data_length < 0 || cfg->data_length > 65535) return fail(c, LORAB200_ERR_INVALID, "data_length out of range");
+    if (symbols_stride == 0 || symbols_stride > 4096) return fail(c, LORAB200_ERR_UNSUPPORTED, "symbols_stride must be 1..4096");
+    if (bytes_stride == 0 || bytes_stride > (size_t(1) << 20)) return fail(c, LORAB200_ERR_INVALID, "bytes_stride out of range");
+    CU_TRY(c, cudaSetDevice(c->device));
+    DecodeParams p{};
+    p.symbols = symbols_dev;
+    p.n_packets = n_packets;
+    p.sym_stride = unsigned(symbols_stride);
+    p.n_syms = n_symbols_dev;
+    p.cfg.sf = c->sf; p.cfg.ppm = cfg->ppm; p.cfg.rdd = cfg->rdd; p.cfg.explicit_hdr = cfg->explicit_header;
+    p.cfg.hdr = cfg->hdr; p.cfg.data_length = cfg->data_length; p.cfg.crcc = cfg->crcc; p.cfg.error_check = cfg->error_check;
+    p.out = bytes_dev;
+    p.out_stride = unsigned(bytes_stride);
+    p.lengths = lengths_dev;
+    p.max_sym = codec_num_symbols(p.cfg, p.sym_stride);
+    p.max_cw = codec_num_codewords(p.cfg, p.sym_stride);
+    p.max_bytes = (p.max_cw + 1) / 2;
+    const size_t sym_bytes = (size_t(p.max_sym) * 2 * n_packets + 15) & ~size_t(15);
+    const size_t cw_bytes = (size_t(p.max_cw) * n_packets + 15) & ~size_t(15);
+    int st;
+    if ((st = ensure_dev(c, c->d_dec_scratch, sym_bytes + cw_bytes + size_t(p.max_bytes) * n_packets))) return st;
+    char *base = static_cast<char *>(c->d_dec_scratch.p);
+    p.sym_scratch = reinterpret_cast<uint16_t *>(base);
+    p.cw_scratch = reinterpret_cast<uint8_t *>(base + sym_bytes);
+    p.byte_scratch = reinterpret_cast<uint8_t *>(base + sym_bytes + cw_bytes);
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    decode_kernel<<<unsigned((n_packets + 63) / 64), 64, 0, s>>>(p);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    c->last_kernel = "decode";
     return LORAB200_OK;
 }
 

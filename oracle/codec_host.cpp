@@ -1,0 +1,22 @@
+/* codec_host.cpp -- TEST INFRASTRUCTURE ONLY.  Builds the product's symbol->byte codec
+ * (lora-sdr_b200/csrc/codec.h, a host+device header) for the HOST, so that its logic can be
+ * compared with the unmodified reference decoder on a machine without a GPU.  The product
+ * itself only decodes on the device (lorab200_decode_dev). */
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../lora-sdr_b200/csrc/codec.h"
+
+extern "C" int codec_host_decode(const int32_t *cfg8 /* sf, ppm, rdd, explicit, hdr, data_length, crcc, error_check */,
+                                 const uint16_t *symbols, int n_symbols, uint8_t *out, int out_cap)
+{
+    lorab200::DecoderCfg c;
+    c.sf = cfg8[0]; c.ppm = cfg8[1]; c.rdd = cfg8[2]; c.explicit_hdr = cfg8[3];
+    c.hdr = cfg8[4]; c.data_length = cfg8[5]; c.crcc = cfg8[6]; c.error_check = cfg8[7];
+    const unsigned n = unsigned(n_symbols < 0 ? 0 : n_symbols);
+    std::vector<uint16_t> sym(lorab200::codec_num_symbols(c, n) + 16);
+    std::memcpy(sym.data(), symbols, size_t(n) * 2);
+    std::vector<uint8_t> cw(lorab200::codec_num_codewords(c, n) + 16), bytes(cw.size() / 2 + 16);
+    return lorab200::decode_packet(c, sym.data(), n, cw.data(), bytes.data(), out, unsigned(out_cap));
+}

@@ -250,6 +250,49 @@ int loopback_mod(const LoopCfg *cfg, const unsigned short *syms, int n_syms,
     }
 }
 
+/* Decoder only: one packet of demodulated symbols -> bytes, by the reference LoRaDecoder with every
+ * setter exposed.  cfg8 = sf, ppm, rdd, explicit, hdr, data_length, crcc, error_check.
+ * *length = payload length, or -1 when the decoder dropped the packet, -2 when it produced nothing. */
+int loopback_decode(const int *cfg8, const unsigned short *syms, int n_syms, unsigned char *out, int out_cap,
+                    int *length, char *err256)
+{
+    try
+    {
+        static const char *crs[] = {"4/4", "4/5", "4/6", "4/7", "4/8"};
+        std::unique_ptr<Pothos::Block> decoder(Pothos::BlockRegistry::make("/lora/lora_decoder"));
+        decoder->call("setSpreadFactor", size_t(cfg8[0]));
+        decoder->call("setSymbolSize", size_t(cfg8[1]));
+        decoder->call("setCodingRate", std::string(crs[cfg8[2]]));
+        decoder->call("enableExplicit", bool(cfg8[3] != 0));
+        decoder->call("enableHdr", bool(cfg8[4] != 0));
+        decoder->call("setDataLength", size_t(cfg8[5]));
+        decoder->call("enableCrcc", bool(cfg8[6] != 0));
+        decoder->call("enableErrorCheck", bool(cfg8[7] != 0));
+        ministream::Topology topology;
+        decoder->output("0")->collect = true;
+        topology.add(decoder.get());
+        topology.commit();
+        Pothos::Packet pkt;
+        pkt.payload = Pothos::BufferChunk(typeid(uint16_t), size_t(n_syms));
+        std::memcpy(pkt.payload.as<void *>(), syms, size_t(n_syms) * 2);
+        ministream::Topology::feedMessage(decoder.get(), "0", Pothos::Object(pkt));
+        topology.run();
+        const auto &msgs = decoder->output("0")->collectedMessages;
+        const unsigned long long dropped = decoder->call<unsigned long long>("getDropped");
+        if (msgs.empty()) { *length = dropped ? -1 : -2; return 0; }
+        const auto &o = msgs[0].extract<Pothos::Packet>();
+        if (int(o.payload.length) > out_cap) throw Pothos::Exception("loopback_decode", "out too small");
+        std::memcpy(out, o.payload.as<const void *>(), o.payload.length);
+        *length = int(o.payload.length);
+        return 0;
+    }
+    catch (const std::exception &ex)
+    {
+        std::strncpy(err256, ex.what(), 255);
+        return -1;
+    }
+}
+
 /* Receive side: the SAME IQ samples -> DEMOD (reference or ours) -> decoder.
  * `feed` samples are appended to the demod's input per scheduler pass (0 = all at once). */
 int loopback_rx(const LoopCfg *cfg, const float *iq, unsigned long long n_samples, unsigned long long feed, LoopOut *out)

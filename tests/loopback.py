@@ -35,6 +35,7 @@ def _lib():
     L.loopback_rx.argtypes = [C.POINTER(LoopCfg), C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.POINTER(LoopOut)]
     L.loopback_encode.argtypes = [C.POINTER(LoopCfg), C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                   C.c_char_p]
+    L.loopback_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_char_p]
     L.loopback_mod.argtypes = [C.POINTER(LoopCfg), C.c_void_p, C.c_int, C.c_void_p, C.c_ulonglong,
                                C.POINTER(C.c_ulonglong), C.c_char_p]
     return L
@@ -50,6 +51,21 @@ def encode(sf, cr, payload):
     if L.loopback_encode(C.byref(cfg), payload, len(payload), syms.ctypes.data_as(C.c_void_p), syms.size, C.byref(n), err):
         raise RuntimeError(err.value.decode())
     return syms[: n.value].copy()
+
+
+def decode(cfg8, syms):
+    """one packet of symbols -> (length, bytes) by the reference LoRaDecoder; cfg8 = (sf, ppm, rdd, explicit, hdr,
+    data_length, crcc, error_check).  length -1 = dropped, -2 = nothing produced."""
+    L = _lib()
+    cfg = (C.c_int * 8)(*[int(v) for v in cfg8])
+    syms = np.ascontiguousarray(syms, np.uint16)
+    out = np.zeros(8192, np.uint8)
+    n = C.c_int()
+    err = C.create_string_buffer(256)
+    if L.loopback_decode(cfg, syms.ctypes.data_as(C.c_void_p), syms.size, out.ctypes.data_as(C.c_void_p), out.size,
+                         C.byref(n), err):
+        raise RuntimeError(err.value.decode())
+    return n.value, bytes(out[: max(n.value, 0)])
 
 
 def modulate(sf, syms, padding=1, sync=0x12, ampl=1.0, ovs=1):

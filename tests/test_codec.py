@@ -1,0 +1,101 @@
+"""Row f4 on the CPU: the product's symbols -> bytes codec (lora-sdr_b200/csrc/codec.h, built for
+the host by oracle/codec_host.cpp) against the UNMODIFIED reference LoRaDecoder.cpp run through
+the ministream harness -- every setter combination, clean packets from the reference encoder,
+packets with symbol errors, truncated packets and plain garbage.  Lengths, drop decisions and
+bytes must be identical.  (The GPU test, tests/test_gpu_decode.py, then checks the device build
+of the same header against both.)"""
+import ctypes as C
+import itertools
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import loopback
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB = ROOT / "oracle" / "libcodec_host.so"
+
+needs_chain = pytest.mark.skipif(not loopback.available(), reason="oracle/_ref/libloraloop.so not built")
+
+
+def host_codec():
+    if not LIB.exists():
+        subprocess.run(["make", "-C", str(ROOT / "oracle"), "libcodec_host.so"], check=True, capture_output=True)
+    L = C.CDLL(str(LIB))
+    L.codec_host_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    return L
+
+
+def host_decode(L, cfg8, syms):
+    cfg = (C.c_int32 * 8)(*[int(v) for v in cfg8])
+    syms = np.ascontiguousarray(syms, np.uint16)
+    out = np.zeros(8192, np.uint8)
+    n = L.codec_host_decode(cfg, syms.ctypes.data_as(C.c_void_p), syms.size, out.ctypes.data_as(C.c_void_p), out.size)
+    return n, bytes(out[: max(n, 0)])
+
+
+def configs():
+    """(sf, ppm, rdd, explicit, hdr, data_length, crcc, error_check)"""
+    for sf, rdd in itertools.product((7, 9, 12), range(5)):
+        for ppm in (0, sf - 2):
+            for explicit, hdr, crcc, echk in itertools.product((1, 0), (0, 1), (0, 1), (0, 1)):
+                if not explicit and hdr:
+                    continue
+                yield (sf, ppm, rdd, explicit, hdr, 11, crcc, echk)
+
+
+@needs_chain
+def test_codec_matches_reference_decoder_on_encoder_output_and_corruptions():
+    L = host_codec()
+    rng = np.random.default_rng(2024)
+    checked = dropped = 0
+    for cfg in configs():
+        sf, ppm, rdd, explicit, hdr, dlen, crcc, echk = cfg
+        if ppm:
+            continue                       # the driver's encoder entry point has no symbol-size setter
+        payload = bytes(rng.integers(0, 256, dlen, dtype=np.uint8))
+        syms = loopback.encode(sf, rdd, payload)            # explicit header, no CRC, rate rdd
+        variants = [syms]
+        for _ in range(3):                                  # symbol errors (off-by-one and random)
+            s = syms.copy()
+            k = rng.integers(0, s.size, rng.integers(1, 4))
+            s[k] = (s[k] + rng.choice([1, (1 << sf) - 1, int(rng.integers(1, 1 << sf))])) % (1 << sf)
+            variants.append(s)
+        variants.append(syms[: max(8, syms.size - 3)])      # truncated
+        variants.append(syms[:5])                           # shorter than a header: ignored
+        for s in variants:
+            exp = loopback.decode(cfg, s)
+            got = host_decode(L, cfg, s)
+            assert got == exp, (cfg, list(s[:12]), got, exp)
+            checked += 1
+            dropped += exp[0] == -1
+        if explicit and not crcc and not hdr:
+            assert loopback.decode(cfg, syms)[1][: dlen - 2] == payload[: dlen - 2]   # (the reference trims 5 bytes)
+    assert checked > 500 and dropped > 10
+
+
+@needs_chain
+def test_codec_matches_reference_decoder_on_random_symbols():
+    """Garbage in: header fields, lengths, CRC and parity paths are all exercised by random symbols."""
+    L = host_codec()
+    rng = np.random.default_rng(7)
+    outcomes = {"ok": 0, "dropped": 0, "ignored": 0}
+    for cfg in configs():
+        sf = cfg[0]
+        for n in (8, 13, 40, 83):
+            s = rng.integers(0, 1 << sf, n).astype(np.uint16)
+            got = host_decode(L, cfg, s)
+            try:
+                exp = loopback.decode(cfg, s)
+            except RuntimeError as e:
+                # explicit header, hdr off, decoded length < 2 (or 5 with CRC): the reference computes
+                # dataLength -= 5 on a size_t and dies allocating the result (LoRaDecoder.cpp:381-384,393);
+                # ours reports the underflow as "no room"
+                assert "bad_alloc" in str(e) and got[0] == -3, (cfg, n, got[0], str(e))
+                outcomes["underflow"] = outcomes.get("underflow", 0) + 1
+                continue
+            assert got == exp, (cfg, n, got[0], exp[0])
+            outcomes["ok" if exp[0] >= 0 else ("dropped" if exp[0] == -1 else "ignored")] += 1
+    assert outcomes["ok"] > 100 and outcomes["dropped"] > 100

@@ -1,0 +1,99 @@
+"""Row f4 on the GPU: lorab200_decode_dev (one packet per thread, the device build of codec.h)
+against the unmodified reference LoRaDecoder.cpp: a batch that mixes clean packets from the
+reference encoder, corrupted ones, truncated ones and random symbols, with per-packet lengths;
+every length / drop decision / byte must be identical.  Then the whole receive chain on the
+device: reference-encoded packets -> GPU modulator -> GPU demod -> GPU decoder -> payload."""
+import numpy as np
+import pytest
+
+import loopback
+
+pytestmark = pytest.mark.gpu
+needs_chain = pytest.mark.skipif(not loopback.available(), reason="oracle/_ref/libloraloop.so not built")
+
+
+def _batch(sf, rdd, rng, n_clean=6, n_rand=10):
+    packets = []
+    for _ in range(n_clean):
+        payload = bytes(rng.integers(0, 256, int(rng.integers(2, 40)), dtype=np.uint8))
+        s = loopback.encode(sf, rdd, payload)
+        packets.append(s)
+        bad = s.copy()
+        k = rng.integers(0, s.size, 2)
+        bad[k] = (bad[k] + int(rng.integers(1, 1 << sf))) % (1 << sf)
+        packets.append(bad)
+        packets.append(s[: max(8, s.size - int(rng.integers(1, 6)))])
+    for _ in range(n_rand):
+        packets.append(rng.integers(0, 1 << sf, int(rng.integers(3, 90))).astype(np.uint16))
+    return packets
+
+
+@needs_chain
+@pytest.mark.parametrize("sf,rdd,explicit,hdr,crcc,echk,ppm", [
+    (7, 4, 1, 0, 0, 0, 0), (7, 1, 1, 1, 1, 1, 0), (9, 0, 1, 0, 0, 1, 0), (9, 2, 0, 0, 1, 0, 7),
+    (10, 3, 1, 1, 0, 0, 0), (12, 4, 0, 0, 0, 1, 10), (12, 2, 1, 0, 1, 0, 0), (8, 3, 0, 0, 0, 0, 0)])
+def test_decode_dev_matches_reference_decoder(lib, cuda_ok, sf, rdd, explicit, hdr, crcc, echk, ppm):
+    import torch
+    rng = np.random.default_rng(sf * 100 + rdd * 10 + explicit)
+    packets = _batch(sf, rdd, rng)
+    stride = max(p.size for p in packets)
+    host = np.zeros((len(packets), stride), np.uint16)
+    lens = np.zeros(len(packets), np.int32)
+    for i, p in enumerate(packets):
+        host[i, : p.size] = p
+        host[i, p.size:] = 0xFFFF                       # garbage after the valid symbols must be ignored
+        lens[i] = p.size
+    cfg = (sf, ppm, rdd, explicit, hdr, 9, crcc, echk)
+    d = lib.Demod(sf)
+    out, got_len = d.decode_dev(torch.from_numpy(host.view(np.int16)).cuda(), torch.from_numpy(lens).cuda(),
+                                ppm=ppm, rdd=rdd, explicit_header=bool(explicit), hdr=bool(hdr), data_length=9,
+                                crcc=bool(crcc), error_check=bool(echk), bytes_stride=512)
+    assert d.last_kernel == "decode"
+    out, got_len = out.cpu().numpy(), got_len.cpu().numpy()
+    seen = set()
+    for i, p in enumerate(packets):
+        try:
+            exp_len, exp = loopback.decode(cfg, p)
+        except RuntimeError as e:                       # the reference's own size_t underflow (see tests/test_codec.py)
+            assert "bad_alloc" in str(e) and got_len[i] == -3
+            continue
+        assert got_len[i] == exp_len, (i, p.size, got_len[i], exp_len)
+        if exp_len > 0:
+            assert bytes(out[i, :exp_len]) == exp
+        seen.add("ok" if exp_len >= 0 else exp_len)
+    if explicit and not crcc:
+        assert "ok" in seen            # (with the CRC check on, packets made without a CRC are all dropped)
+    assert len(seen) >= 1
+    d.close()
+
+
+@needs_chain
+@pytest.mark.parametrize("sf", [7, 10])
+def test_whole_receive_chain_on_the_device(lib, cuda_ok, sf):
+    """reference encoder -> lorab200_mod_dev (ideal) -> lorab200_demod_dev on the data symbols ->
+    lorab200_decode_dev: the payloads come back, nothing leaves the GPU in between."""
+    import torch
+    rng = np.random.default_rng(sf)
+    n = 1 << sf
+    payloads = [bytes(rng.integers(0, 256, 20, dtype=np.uint8)) for _ in range(8)]
+    syms = np.stack([loopback.encode(sf, 4, p) for p in payloads])
+    d = lib.Demod(sf)
+    iq = d.mod_dev(torch.from_numpy(syms.astype(np.int16)).cuda(), padding=1, ampl=1.0, mode=lib.MOD_IDEAL)
+    nsy = syms.shape[1]
+    head = 14 * n + n // 4                                   # preamble, sync, down-chirps, quarter chirp
+    data = iq[:, head: head + nsy * n].contiguous()
+    res, _, _, _ = d.demod_dev(data.reshape(-1), len(payloads) * nsy)
+    torch.cuda.synchronize()
+    idx = lib.results_to_numpy(res)["index"].reshape(len(payloads), nsy)
+    # without the receiver's sync stage the detected bin is the symbol plus one constant (the modulator's
+    # chirp law starts one frequency step in, ChirpGenerator.hpp:33 "f += fStep" before the first sample)
+    off = int(idx[0, 0] - syms[0, 0]) % n
+    assert off in (0, 1) and np.array_equal((idx - off) % n, syms)
+    idx = (idx - off) % n
+    out, lens = d.decode_dev(torch.from_numpy(idx.astype(np.int16)).cuda(), rdd=4)
+    out, lens = out.cpu().numpy(), lens.cpu().numpy()
+    for i, p in enumerate(payloads):
+        ref_len, ref = loopback.decode((sf, 0, 4, 1, 0, 8, 0, 0), syms[i])
+        assert lens[i] == ref_len and bytes(out[i, : lens[i]]) == ref
+        assert ref[: len(p) - 2] == p[: len(p) - 2]
+    d.close()
