@@ -235,6 +235,44 @@ int lorab200_mod_dev(lorab200_ctx *ctx, const uint16_t *symbols_dev, size_t n_pa
                      size_t syms_per_packet, unsigned sync, size_t padding, float ampl, int ovs,
                      int mode, void *iq_dev, void *cuda_stream);
 
+/* ---- receiver: sync acquisition + symbol extraction on the device (row f3) -- */
+
+/* The members of LoRaDemod that survive a work() call (LoRaDemod.cpp:362-392).  All zero is the
+ * state after activate(). */
+typedef struct lorab200_rx_state {
+    int32_t phase, table, sym_count, prev_value, freq_error, fine_index;
+    float ffe;
+    int32_t sig_error;
+    float sig_power, sig_snr;
+} lorab200_rx_state;
+
+typedef struct lorab200_rx_packet {
+    int32_t length;       /* symbols in the packet (the Packet's payload.length / 2) */
+    int32_t error;        /* the "error" signal emitted for this packet (LoRaDemod.cpp:267) */
+    float power, snr;     /* the "power" and "snr" signals (:268-269) */
+} lorab200_rx_packet;
+
+/*
+ * Run the reference demod block's whole work() sequence -- frame sync, sync word, down-chirps,
+ * quarter chirp, data symbols (LoRaDemod.cpp:145-327) -- over n_channels independent IQ
+ * streams in ONE launch, one CTA per channel, no host round trip per window.  Channel c reads
+ * iq_dev + c*channel_stride_samples, n_samples samples; it stops when fewer than 2N samples
+ * remain (consumed_dev[c] says how far it got: re-present the tail at the start of the next
+ * call's buffer) or when max_packets packets have been written.
+ *   state_dev    [n_channels] in/out; zero it (cudaMemset) for a fresh stream
+ *   partial_dev  [n_channels][mtu] in/out scratch: the packet under construction between calls
+ *   symbols_dev  [n_channels][max_packets][mtu] int16: packet p of channel c, info_dev[c][p].length symbols
+ *   setSync / setThreshold / setMTU are the sync, thresh_db, mtu arguments.
+ * Symbols, packet boundaries and the error signal are bit-identical to the reference block's;
+ * power/snr use the device log10f (within 1e-4 dB), so a squelch decision can differ only when
+ * snr is within that distance of thresh_db.  Asynchronous on cuda_stream.
+ */
+int lorab200_rx_dev(lorab200_ctx *ctx, const void *iq_dev, size_t n_channels, size_t channel_stride_samples,
+                    size_t n_samples, unsigned sync, float thresh_db, size_t mtu,
+                    lorab200_rx_state *state_dev, int16_t *partial_dev, int16_t *symbols_dev,
+                    lorab200_rx_packet *info_dev, int32_t *n_packets_dev, uint64_t *consumed_dev,
+                    size_t max_packets, void *cuda_stream);
+
 /* ---- decoder ------------------------------------- */
 
 /* The setters of /lora/lora_decoder (LoRaDecoder.cpp:137-183); interleaving is always on (the

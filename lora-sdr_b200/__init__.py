@@ -52,7 +52,7 @@ EXPORTS = [
     "lorab200_gen_chirp", "lorab200_demod_dev", "lorab200_demod_host", "lorab200_pack_symbols",
     "lorab200_kernel_launches", "lorab200_last_kernel", "lorab200_alloc_pinned",
     "lorab200_free_pinned", "lorab200_table_len", "lorab200_build_table", "lorab200_fine_advance",
-    "lorab200_demod_multi_dev", "lorab200_mod_samples", "lorab200_mod_dev", "lorab200_decode_dev",
+    "lorab200_demod_multi_dev", "lorab200_mod_samples", "lorab200_mod_dev", "lorab200_decode_dev", "lorab200_rx_dev",
 ]
 
 
@@ -143,6 +143,7 @@ def load_library() -> C.CDLL:
     L.lorab200_demod_host.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp, vp, vp]
     L.lorab200_demod_multi_dev.argtypes = [vp, C.POINTER(vp), sz, sz, sz, C.c_int, vp, vp]
     L.lorab200_decode_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, vp, vp]
+    L.lorab200_rx_dev.argtypes = [vp, vp, sz, sz, sz, C.c_uint, C.c_float, sz, vp, vp, vp, vp, vp, vp, sz, vp]
     L.lorab200_mod_samples.restype = sz
     L.lorab200_mod_samples.argtypes = [C.c_int, C.c_int, sz, sz]
     L.lorab200_mod_dev.argtypes = [vp, vp, sz, sz, C.c_uint, sz, C.c_float, C.c_int, C.c_int, vp, vp]
@@ -315,6 +316,34 @@ class Demod:
                                              C.c_void_p(out.data_ptr()), C.c_void_p(stream))
         self._check(st, "demod_multi_dev")
         return out
+
+    # ---- receiver: frame sync + symbol extraction on the device (LoRaDemod.cpp:145-327) -----------------
+    def rx_dev(self, iq, n_samples=None, sync=0x12, thresh=-30.0, mtu=256, max_packets=16, state=None, stream=None):
+        """iq: CUDA complex64 tensor [n_channels, samples].  Returns a dict of CUDA tensors: symbols
+        [n_channels, max_packets, mtu] int16, info [n_channels, max_packets, 4] int32 words (length, error, power
+        bits, snr bits), n_packets [n_channels], consumed [n_channels], state (pass it back in to continue)."""
+        import torch
+
+        assert iq.is_cuda and iq.is_contiguous() and iq.dim() == 2
+        nch, stride = iq.shape
+        n_samples = stride if n_samples is None else int(n_samples)
+        dev = iq.device
+        if state is None:
+            state = {"state": torch.zeros((nch, 10), dtype=torch.int32, device=dev),
+                     "partial": torch.zeros((nch, mtu), dtype=torch.int16, device=dev)}
+        symbols = torch.zeros((nch, max_packets, mtu), dtype=torch.int16, device=dev)
+        info = torch.zeros((nch, max_packets, 4), dtype=torch.int32, device=dev)
+        n_packets = torch.zeros(nch, dtype=torch.int32, device=dev)
+        consumed = torch.zeros(nch, dtype=torch.int64, device=dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        st = self.L.lorab200_rx_dev(self.ctx, C.c_void_p(iq.data_ptr()), nch, stride, n_samples, sync, thresh, mtu,
+                                    C.c_void_p(state["state"].data_ptr()), C.c_void_p(state["partial"].data_ptr()),
+                                    C.c_void_p(symbols.data_ptr()), C.c_void_p(info.data_ptr()),
+                                    C.c_void_p(n_packets.data_ptr()), C.c_void_p(consumed.data_ptr()), max_packets,
+                                    C.c_void_p(stream))
+        self._check(st, "rx_dev")
+        return dict(symbols=symbols, info=info, n_packets=n_packets, consumed=consumed, state=state)
 
     # ---- decoder (LoRaDecoder.cpp) ----------------------------------------------------------------
     def decode_dev(self, symbols, n_symbols=None, ppm=0, rdd=4, explicit_header=True, hdr=False, data_length=8,

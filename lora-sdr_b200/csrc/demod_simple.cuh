@@ -34,6 +34,87 @@ __device__ __forceinline__ int kiss_input_index(int j)
 
 constexpr int kSimpleThreads = 128;
 
+// One window, cooperatively by a CTA of kSimpleThreads threads: dechirp (+ optional fine-tune
+// multiply: fidx[i] per sample when `walk`, else the constant index idx_const), kissfft's stages
+// in shared memory, peak scan.  F: N float2 of shared memory; s_*: kSimpleThreads/32 entries each.
+// The raw record is returned in thread 0 (other threads: unspecified).  Ends with a
+// __syncthreads, so F and the scratch may be reused at once.
+template <int SF>
+__device__ __forceinline__ RawResult simple_window(const float2 *__restrict__ in, const float2 *__restrict__ chirp,
+                                                   const float2 *__restrict__ fine, const int *fidx, int idx_const,
+                                                   bool walk, const float2 *__restrict__ tw, float2 *dec_out,
+                                                   float2 *fft_out, float2 *F, float *s_val, int *s_idx, double *s_sum)
+{
+    constexpr int N = 1 << SF;
+    constexpr int T = kSimpleThreads;
+    const int tid = threadIdx.x;
+
+    // dechirp + digit-reversed load
+    for (int j = tid; j < N; j += T) {
+        const int i = kiss_input_index<SF>(j);
+        float2 d = cx_mul(in[i], chirp[i]);
+        if (fine) d = cx_mul(d, fine[walk ? fidx[i] : idx_const]);
+        if (dec_out) dec_out[i] = d;
+        F[j] = d;
+    }
+
+    // stages, deepest first: radix-2 (odd SF) with m=1, then radix-4 with m=..,
+    int m = 1;
+    if (SF & 1) {
+        __syncthreads();
+        for (int b = tid; b < N / 2; b += T) {
+            float2 a0 = F[2 * b], a1 = cx_mul(F[2 * b + 1], tw[0]);
+            bfly2(a0, a1);
+            F[2 * b] = a0; F[2 * b + 1] = a1;
+        }
+        m = 2;
+    }
+    for (; m < N; m <<= 2) {
+        __syncthreads();
+        const int fstride = N / (4 * m);
+        for (int b = tid; b < N / 4; b += T) {
+            const int k = b & (m - 1);
+            const int base = (b - k) * 4 + k;
+            float2 a0 = F[base];
+            float2 a1 = cx_mul(F[base + m], tw[k * fstride]);
+            float2 a2 = cx_mul(F[base + 2 * m], tw[2 * k * fstride]);
+            float2 a3 = cx_mul(F[base + 3 * m], tw[3 * k * fstride]);
+            bfly4(a0, a1, a2, a3);
+            F[base] = a0; F[base + m] = a1; F[base + 2 * m] = a2; F[base + 3 * m] = a3;
+        }
+    }
+    __syncthreads();
+
+    // peak scan (LoRaDetector.hpp:33-48): strict '>' from 0, first max wins
+    float bv = 0.0f; int bi = 0; double sum = 0.0;
+    for (int j = tid; j < N; j += T) {
+        const float2 v = F[j];
+        if (fft_out) fft_out[j] = v;
+        const float m2 = cx_mag2(v);
+        sum += double(m2);
+        if (m2 > bv) { bv = m2; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_down_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+        argmax_merge(bv, bi, ov, oi);
+    }
+    if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; s_sum[tid >> 5] = sum; }
+    __syncthreads();
+    RawResult r;
+    r.index = 0; r.max_mag2 = 0.0f; r.total = 0.0; r.left = make_float2(0.f, 0.f); r.right = make_float2(0.f, 0.f);
+    if (tid == 0) {
+        for (int k = 1; k < T / 32; ++k) { argmax_merge(bv, bi, s_val[k], s_idx[k]); sum += s_sum[k]; }
+        r.index = bi; r.max_mag2 = bv; r.total = sum;
+        r.left = F[bi > 0 ? bi - 1 : N - 1];
+        r.right = F[bi < N - 1 ? bi + 1 : 0];
+    }
+    __syncthreads();
+    return r;
+}
+
 template <int SF, bool MULTI>
 __global__ void __launch_bounds__(kSimpleThreads)
 demod_simple_kernel(const DemodParams p, const SegList<MULTI> segs)
@@ -66,72 +147,13 @@ demod_simple_kernel(const DemodParams p, const SegList<MULTI> segs)
             }
             __syncthreads();
         }
-        const int idx_const = p.fine_index0;
-
-        // dechirp + digit-reversed load
-        for (int j = tid; j < N; j += T) {
-            const int i = kiss_input_index<SF>(j);
-            float2 d = cx_mul(in[i], p.chirp[i]);
-            if (fine) d = cx_mul(d, p.fine[walk ? fidx[i] : idx_const]);
-            if (p.dec) p.dec[w * N + i] = d;
-            F[j] = d;
-        }
-
-        // stages, deepest first: radix-2 (odd SF) with m=1, then radix-4 with m=..,
-        int m = 1;
-        if (SF & 1) {
-            __syncthreads();
-            for (int b = tid; b < N / 2; b += T) {
-                float2 a0 = F[2 * b], a1 = cx_mul(F[2 * b + 1], p.tw[0]);
-                bfly2(a0, a1);
-                F[2 * b] = a0; F[2 * b + 1] = a1;
-            }
-            m = 2;
-        }
-        for (; m < N; m <<= 2) {
-            __syncthreads();
-            const int fstride = N / (4 * m);
-            for (int b = tid; b < N / 4; b += T) {
-                const int k = b & (m - 1);
-                const int base = (b - k) * 4 + k;
-                float2 a0 = F[base];
-                float2 a1 = cx_mul(F[base + m], p.tw[k * fstride]);
-                float2 a2 = cx_mul(F[base + 2 * m], p.tw[2 * k * fstride]);
-                float2 a3 = cx_mul(F[base + 3 * m], p.tw[3 * k * fstride]);
-                bfly4(a0, a1, a2, a3);
-                F[base] = a0; F[base + m] = a1; F[base + 2 * m] = a2; F[base + 3 * m] = a3;
-            }
-        }
-        __syncthreads();
-
-        // peak scan (LoRaDetector.hpp:33-48): strict '>' from 0, first max wins
-        float bv = 0.0f; int bi = 0; double sum = 0.0;
-        for (int j = tid; j < N; j += T) {
-            const float2 v = F[j];
-            if (p.fft) p.fft[w * N + j] = v;
-            const float m2 = cx_mag2(v);
-            sum += double(m2);
-            if (m2 > bv) { bv = m2; bi = j; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_down_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-            sum += __shfl_down_sync(0xffffffffu, sum, o);
-            argmax_merge(bv, bi, ov, oi);
-        }
-        if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; s_sum[tid >> 5] = sum; }
-        __syncthreads();
+        const RawResult r = simple_window<SF>(in, p.chirp, p.fine, fidx, p.fine_index0, walk, p.tw,
+                                              p.dec ? p.dec + w * N : nullptr, p.fft ? p.fft + w * N : nullptr,
+                                              F, s_val, s_idx, s_sum);
         if (tid == 0) {
-            for (int k = 1; k < T / 32; ++k) { argmax_merge(bv, bi, s_val[k], s_idx[k]); sum += s_sum[k]; }
-            RawResult r;
-            r.index = bi; r.max_mag2 = bv; r.total = sum;
-            r.left = F[bi > 0 ? bi - 1 : N - 1];
-            r.right = F[bi < N - 1 ? bi + 1 : 0];
             if (p.raw) p.raw[w] = r;
             if (p.out) finalize_device(r, p.power_scale, &p.out[w]);
         }
-        __syncthreads();
     }
 }
 

@@ -27,6 +27,7 @@
 #include "fine_prefix.cuh"
 #include "mod_synth.cuh"
 #include "decode.cuh"
+#include "rx_kernel.cuh"
 #include "finalize.h"
 #include "tables.h"
 
@@ -270,6 +271,27 @@ cudaError_t launch_simple(int sf, const DemodParams &p, cudaStream_t s, int sm_c
     case 12: return launch_simple_sf<12>(p, s, sm_count);
     default: return cudaErrorInvalidValue;
     }
+}
+
+static_assert(sizeof(lorab200_rx_state) == sizeof(RxState) && sizeof(lorab200_rx_packet) == sizeof(RxPacketInfo),
+              "the C structs mirror the kernel's");
+
+template <int SF>
+cudaError_t launch_rx_sf(const RxParams &p, cudaStream_t s, int sm_count)
+{
+    constexpr int N = 1 << SF;
+    const size_t smem = size_t(N) * sizeof(float2) + size_t(N) * sizeof(int);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(rx_kernel<SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    unsigned grid = p.n_channels;
+    const unsigned cap = unsigned(sm_count) * 16u;
+    if (grid > cap) grid = cap;
+    rx_kernel<SF><<<grid, kSimpleThreads, smem, s>>>(p);
+    return cudaGetLastError();
 }
 
 bool stream_capturing(cudaStream_t s)
@@ -650,6 +672,58 @@ int lorab200_demod_multi_dev(lorab200_ctx *c, const void *const *iq_dev_list, si
     }
     if (e != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "kernel launch", e);
     c->launches++;
+    return LORAB200_OK;
+}
+
+int lorab200_rx_dev(lorab200_ctx *c, const void *iq_dev, size_t n_channels, size_t channel_stride_samples,
+                    size_t n_samples, unsigned sync, float thresh_db, size_t mtu, lorab200_rx_state *state_dev,
+                    int16_t *partial_dev, int16_t *symbols_dev, lorab200_rx_packet *info_dev, int32_t *n_packets_dev,
+                    uint64_t *consumed_dev, size_t max_packets, void *cuda_stream)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    c->err.clear();
+    if (n_channels == 0) return LORAB200_OK;
+    if (!iq_dev || !state_dev || !partial_dev || !symbols_dev || !info_dev || !n_packets_dev || !consumed_dev)
+        return fail(c, LORAB200_ERR_INVALID, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(iq_dev) & 7u) != 0) return fail(c, LORAB200_ERR_INVALID, "iq pointer must be 8-byte aligned");
+    if (sync > 0xff) return fail(c, LORAB200_ERR_INVALID, "sync is one byte");
+    if (mtu == 0 || mtu > 32767) return fail(c, LORAB200_ERR_INVALID, "mtu must be 1..32767");
+    if (max_packets == 0 || max_packets > (size_t(1) << 20)) return fail(c, LORAB200_ERR_INVALID, "max_packets out of range");
+    if (n_channels > (size_t(1) << 24)) return fail(c, LORAB200_ERR_UNSUPPORTED, "too many channels");
+    if (n_channels > 1 && channel_stride_samples < n_samples) return fail(c, LORAB200_ERR_INVALID, "channel_stride_samples < n_samples");
+    CU_TRY(c, cudaSetDevice(c->device));
+    RxParams p{};
+    p.iq = static_cast<const float2 *>(iq_dev);
+    p.chan_stride = channel_stride_samples;
+    p.n_samples = n_samples;
+    p.n_channels = unsigned(n_channels);
+    p.up = c->d_table[LORAB200_TABLE_UP];
+    p.down = c->d_table[LORAB200_TABLE_DOWN];
+    p.fine = c->d_table[LORAB200_TABLE_FINE];
+    p.tw = c->d_table[LORAB200_TABLE_TWIDDLE];
+    p.power_scale = c->pscale;
+    p.fine_len = int(c->n * kFineSteps);
+    p.cfg.n = int(c->n); p.cfg.sync = int(sync); p.cfg.thresh = thresh_db; p.cfg.mtu = int(mtu);
+    p.state = reinterpret_cast<RxState *>(state_dev);
+    p.partial = partial_dev;
+    p.symbols = symbols_dev;
+    p.info = reinterpret_cast<RxPacketInfo *>(info_dev);
+    p.n_packets = n_packets_dev;
+    p.consumed = reinterpret_cast<unsigned long long *>(consumed_dev);
+    p.max_packets = unsigned(max_packets);
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    cudaError_t e;
+    switch (c->sf) {
+    case 7: e = launch_rx_sf<7>(p, s, c->sm_count); break;
+    case 8: e = launch_rx_sf<8>(p, s, c->sm_count); break;
+    case 9: e = launch_rx_sf<9>(p, s, c->sm_count); break;
+    case 10: e = launch_rx_sf<10>(p, s, c->sm_count); break;
+    case 11: e = launch_rx_sf<11>(p, s, c->sm_count); break;
+    default: e = launch_rx_sf<12>(p, s, c->sm_count); break;
+    }
+    if (e != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "rx kernel launch", e);
+    c->launches++;
+    c->last_kernel = std::string("rx_sf") + std::to_string(c->sf);
     return LORAB200_OK;
 }
 
