@@ -304,6 +304,31 @@ int lorab200_decode_dev(lorab200_ctx *ctx, const uint16_t *symbols_dev, size_t n
                         const lorab200_decoder_cfg *cfg, uint8_t *bytes_dev, size_t bytes_stride,
                         int32_t *lengths_dev, void *cuda_stream);
 
+/* ---- encoder ---------------------------------------------------------------- */
+
+/* The setters of /lora/lora_encoder (LoRaEncoder.cpp:104-135). */
+typedef struct lorab200_encoder_cfg {
+    int32_t ppm;              /* setSymbolSize, 0 = SF (must be 0 or 5..SF) */
+    int32_t rdd;              /* setCodingRate "4/4".."4/8" -> 0..4 */
+    int32_t explicit_header;  /* enableExplicit */
+    int32_t crc;              /* enableCrc */
+    int32_t whitening;        /* enableWhitening */
+} lorab200_encoder_cfg;
+
+/*
+ * Batched encoder: n_packets payloads (DEVICE memory, packet p at payloads_dev + p*payload_stride,
+ * lengths_dev[p] bytes or payload_stride each when lengths_dev is NULL, at most 255) -> symbols
+ * (uint16, packet p at symbols_dev + p*symbols_stride) and n_symbols_dev[p]
+ * (LORAB200_DECODE_NO_ROOM if symbols_stride is too small).  Replaces LoRaEncoder::work()
+ * (LoRaEncoder.cpp:137-228) bit-exactly, except that the nibbles that pad the codewords up to a
+ * multiple of PPM are zero here and unspecified in the reference (it reads them past the end
+ * of its byte vector).  lorab200_encode_symbols() gives the symbol count for a payload length.
+ */
+size_t lorab200_encode_symbols(int sf, const lorab200_encoder_cfg *cfg, size_t payload_length);
+int lorab200_encode_dev(lorab200_ctx *ctx, const uint8_t *payloads_dev, size_t n_packets, size_t payload_stride,
+                        const int32_t *lengths_dev, const lorab200_encoder_cfg *cfg, uint16_t *symbols_dev,
+                        size_t symbols_stride, int32_t *n_symbols_dev, void *cuda_stream);
+
 /* ---- diagnostics ----------------------------------------------------------- */
 
 const char *lorab200_strerror(int status);

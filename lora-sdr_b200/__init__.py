@@ -52,7 +52,7 @@ EXPORTS = [
     "lorab200_gen_chirp", "lorab200_demod_dev", "lorab200_demod_host", "lorab200_pack_symbols",
     "lorab200_kernel_launches", "lorab200_last_kernel", "lorab200_alloc_pinned",
     "lorab200_free_pinned", "lorab200_table_len", "lorab200_build_table", "lorab200_fine_advance",
-    "lorab200_demod_multi_dev", "lorab200_mod_samples", "lorab200_mod_dev", "lorab200_decode_dev", "lorab200_rx_dev",
+    "lorab200_demod_multi_dev", "lorab200_mod_samples", "lorab200_mod_dev", "lorab200_decode_dev", "lorab200_rx_dev", "lorab200_encode_dev", "lorab200_encode_symbols",
 ]
 
 
@@ -144,6 +144,9 @@ def load_library() -> C.CDLL:
     L.lorab200_demod_multi_dev.argtypes = [vp, C.POINTER(vp), sz, sz, sz, C.c_int, vp, vp]
     L.lorab200_decode_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, vp, vp]
     L.lorab200_rx_dev.argtypes = [vp, vp, sz, sz, sz, C.c_uint, C.c_float, sz, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.lorab200_encode_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, vp, vp]
+    L.lorab200_encode_symbols.restype = sz
+    L.lorab200_encode_symbols.argtypes = [C.c_int, vp, sz]
     L.lorab200_mod_samples.restype = sz
     L.lorab200_mod_samples.argtypes = [C.c_int, C.c_int, sz, sz]
     L.lorab200_mod_dev.argtypes = [vp, vp, sz, sz, C.c_uint, sz, C.c_float, C.c_int, C.c_int, vp, vp]
@@ -344,6 +347,29 @@ class Demod:
                                     C.c_void_p(stream))
         self._check(st, "rx_dev")
         return dict(symbols=symbols, info=info, n_packets=n_packets, consumed=consumed, state=state)
+
+    # ---- encoder (LoRaEncoder.cpp) ----------------------------------------------------------------
+    def encode_dev(self, payloads, lengths=None, ppm=0, rdd=4, explicit_header=True, crc=True, whitening=True,
+                   symbols_stride=None, stream=None):
+        """payloads: CUDA uint8 tensor [n_packets, stride]; lengths: optional CUDA int32 [n_packets].
+        Returns (symbols int16 [n_packets, symbols_stride], n_symbols int32 [n_packets])."""
+        import torch
+
+        assert payloads.is_cuda and payloads.is_contiguous() and payloads.dim() == 2 and payloads.dtype == torch.uint8
+        npk, stride = payloads.shape
+        cfg = (C.c_int32 * 5)(ppm, rdd, int(explicit_header), int(crc), int(whitening))
+        if symbols_stride is None:
+            symbols_stride = int(self.L.lorab200_encode_symbols(self.sf, C.cast(cfg, C.c_void_p), stride))
+        out = torch.zeros((npk, symbols_stride), dtype=torch.int16, device=payloads.device)
+        nsy = torch.empty(npk, dtype=torch.int32, device=payloads.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(payloads.device).cuda_stream
+        st = self.L.lorab200_encode_dev(self.ctx, C.c_void_p(payloads.data_ptr()), npk, stride,
+                                        C.c_void_p(lengths.data_ptr()) if lengths is not None else None,
+                                        C.cast(cfg, C.c_void_p), C.c_void_p(out.data_ptr()), symbols_stride,
+                                        C.c_void_p(nsy.data_ptr()), C.c_void_p(stream))
+        self._check(st, "encode_dev")
+        return out, nsy
 
     # ---- decoder (LoRaDecoder.cpp) ----------------------------------------------------------------
     def decode_dev(self, symbols, n_symbols=None, ppm=0, rdd=4, explicit_header=True, hdr=False, data_length=8,

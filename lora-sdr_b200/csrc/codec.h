@@ -284,4 +284,104 @@ LB_HD int decode_packet(const DecoderCfg &c, uint16_t *sym_io, unsigned n_in, ui
     return int(data_len);
 }
 
+// ---- encoder (LoRaEncoder.cpp:137-228): payload bytes -> symbols ----------------------------
+struct EncoderCfg {
+    int sf;            // setSpreadFactor
+    int ppm;           // setSymbolSize, 0 = sf
+    int rdd;           // setCodingRate
+    int explicit_hdr;  // enableExplicit
+    int crc;           // enableCrc
+    int whitening;     // enableWhitening
+};
+
+LB_HD unsigned codec_enc_codewords(const EncoderCfg &c, unsigned payload_len)
+{
+    const unsigned ppm = unsigned(c.ppm ? c.ppm : c.sf);
+    return codec_round_up((payload_len + (c.crc ? 2u : 0u)) * 2u + (c.explicit_hdr ? unsigned(kHeaderCodewords) : 0u), ppm); // :186
+}
+LB_HD unsigned codec_enc_symbols(const EncoderCfg &c, unsigned payload_len)
+{
+    const unsigned ppm = unsigned(c.ppm ? c.ppm : c.sf);
+    return unsigned(kHeaderSymbols) + (codec_enc_codewords(c, payload_len) / ppm - 1u) * (4u + unsigned(c.rdd));              // :187
+}
+
+// LoRaCodes.hpp:190-204 / :250-262 / :309-313 / :329-333: the encoders of the four codes
+LB_HD uint8_t codec_encode_nibble(uint8_t x, int rdd)
+{
+    const unsigned d0 = x & 1u, d1 = (x >> 1) & 1u, d2 = (x >> 2) & 1u, d3 = (x >> 3) & 1u;
+    unsigned b = x & 0xfu;
+    switch (rdd) {
+    case 0: return uint8_t(x);                                   // (the caller passes the nibble)
+    case 1: { unsigned t = x ^ (x >> 2); t = t ^ (t >> 1); return uint8_t((x & 0xf) | ((t << 4) & 0x10)); }
+    case 2: { const unsigned u = x ^ (x >> 1) ^ (x >> 2); const unsigned v = u ^ x ^ (x >> 3);
+              return uint8_t(((u & 1) << 4) | ((v & 1) << 5) | (x & 0xf)); }
+    case 3: b |= (d0 ^ d1 ^ d2) << 4; b |= (d1 ^ d2 ^ d3) << 5; b |= (d0 ^ d1 ^ d3) << 6; return uint8_t(b);
+    default: b |= (d0 ^ d1 ^ d2) << 4; b |= (d1 ^ d2 ^ d3) << 5; b |= (d0 ^ d1 ^ d3) << 6; b |= (d0 ^ d2 ^ d3) << 7; return uint8_t(b);
+    }
+}
+
+// LoRaCodes.hpp:336-351: codeword bit k of a block goes to symbol k, rotated by k
+LB_HD void codec_interleave(const uint8_t *cw, unsigned n_cw, uint16_t *sym, unsigned ppm, unsigned rdd)
+{
+    const unsigned per = 4 + rdd;
+    for (unsigned x = 0; x < n_cw / ppm; x++)
+        for (unsigned k = 0; k < per; k++) {
+            unsigned s = sym[x * per + k];
+            for (unsigned m = 0; m < ppm; m++) s |= ((unsigned(cw[x * ppm + (m + k) % ppm]) >> k) & 1u) << m;
+            sym[x * per + k] = uint16_t(s);
+        }
+}
+
+// LoRaEncoder.cpp:137-228.  `bytes` : payload_len + 2 bytes of scratch, `cw`: codec_enc_codewords()
+// bytes of scratch, `sym`: codec_enc_symbols() outputs.  Nibbles past the end of the payload (the
+// padding that rounds the codewords up to a multiple of PPM) are ZERO here; the reference reads them
+// from beyond its byte vector (LoRaEncoder.cpp:141-146 with count > what is left), i.e. they are
+// unspecified there.  Returns the number of symbols.
+LB_HD int encode_packet(const EncoderCfg &c, const uint8_t *payload, unsigned payload_len, uint8_t *bytes,
+                        uint8_t *cw, uint16_t *sym)
+{
+    const unsigned sf = unsigned(c.sf), ppm = unsigned(c.ppm ? c.ppm : c.sf);
+    const unsigned total = payload_len + (c.crc ? 2u : 0u);
+    const unsigned n_cw = codec_enc_codewords(c, payload_len), n_sym = codec_enc_symbols(c, payload_len);
+    for (unsigned i = 0; i < payload_len; i++) bytes[i] = payload[i];
+    if (c.crc) {
+        const uint16_t crc = codec_data_checksum(bytes, int(payload_len));
+        bytes[payload_len] = uint8_t(crc);
+        bytes[payload_len + 1] = uint8_t(crc >> 8);
+    }
+    for (unsigned i = 0; i < n_cw; i++) cw[i] = 0;
+    for (unsigned i = 0; i < n_sym; i++) sym[i] = 0;
+    unsigned k = 0, d = 0;
+    if (c.explicit_hdr) {                                                   // :198-211
+        uint8_t h[3];
+        h[0] = uint8_t(payload_len);
+        h[1] = uint8_t((c.crc ? 1 : 0) | (c.rdd << 1));
+        h[2] = codec_header_checksum(h);
+        cw[k++] = codec_encode_nibble(h[0] >> 4, 4);
+        cw[k++] = codec_encode_nibble(h[0] & 0xf, 4);
+        cw[k++] = codec_encode_nibble(h[1] & 0xf, 4);
+        cw[k++] = codec_encode_nibble(h[2] >> 4, 4);
+        cw[k++] = codec_encode_nibble(h[2] & 0xf, 4);
+    }
+    auto nibble = [&](unsigned dd) -> uint8_t {
+        if ((dd >> 1) >= total) return 0;                                   // padding (see above)
+        return (dd & 1) ? uint8_t(bytes[dd >> 1] >> 4) : uint8_t(bytes[dd >> 1] & 0xf);
+    };
+    const unsigned k1 = k;
+    for (; k < ppm; k++, d++) cw[k] = codec_encode_nibble(nibble(d), 4);    // :213  first block: always (8,4)
+    if (c.whitening) codec_dewhiten(cw + k1, ppm - k1, 0, kHeaderRdd);      // :214-216
+    if (n_cw > ppm) {                                                       // :218-224
+        for (; k < n_cw; k++, d++) cw[k] = codec_encode_nibble(nibble(d), c.rdd);
+        if (c.whitening) codec_dewhiten(cw + ppm, n_cw - ppm, int(ppm - k1), c.rdd);
+    }
+    codec_interleave(cw, ppm, sym, ppm, kHeaderRdd);                        // :227-231
+    if (n_cw > ppm) codec_interleave(cw + ppm, n_cw - ppm, sym + kHeaderSymbols, ppm, unsigned(c.rdd));
+    for (unsigned i = 0; i < n_sym; i++) {                                  // :233-237  Gray -> binary, pad the LSBs
+        uint16_t g = sym[i];
+        g = uint16_t(g ^ (g >> 8)); g = uint16_t(g ^ (g >> 4)); g = uint16_t(g ^ (g >> 2)); g = uint16_t(g ^ (g >> 1));
+        sym[i] = uint16_t(g << (sf - ppm));
+    }
+    return int(n_sym);
+}
+
 } // namespace lorab200

@@ -39,4 +39,32 @@ __global__ void decode_kernel(const DecodeParams p)
                                   p.out + pk * p.out_stride, p.out_stride);
 }
 
+// ---- encoder: payload bytes -> symbols, one packet per thread (encode_packet, codec.h) -------
+struct EncodeParams {
+    const uint8_t *payloads;   // [n_packets][payload_stride]
+    unsigned long long n_packets;
+    unsigned int payload_stride;
+    const int32_t *lengths;    // per-packet payload lengths, or nullptr: payload_stride bytes each
+    EncoderCfg cfg;
+    uint16_t *symbols;         // [n_packets][sym_stride]
+    unsigned int sym_stride;
+    int32_t *n_symbols;        // symbols written per packet, or kDecodeNoRoom
+    uint8_t *byte_scratch; unsigned int max_bytes;
+    uint8_t *cw_scratch; unsigned int max_cw;
+};
+
+__global__ void encode_kernel(const EncodeParams p)
+{
+    const unsigned long long pk = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pk >= p.n_packets) return;
+    unsigned len = p.payload_stride;
+    if (p.lengths) {
+        const int32_t v = p.lengths[pk];
+        len = v < 0 ? 0u : (unsigned(v) > p.payload_stride ? p.payload_stride : unsigned(v));
+    }
+    if (codec_enc_symbols(p.cfg, len) > p.sym_stride) { p.n_symbols[pk] = kDecodeNoRoom; return; }
+    p.n_symbols[pk] = encode_packet(p.cfg, p.payloads + pk * p.payload_stride, len, p.byte_scratch + pk * p.max_bytes,
+                                    p.cw_scratch + pk * p.max_cw, p.symbols + pk * p.sym_stride);
+}
+
 } // namespace lorab200

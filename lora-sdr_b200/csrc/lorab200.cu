@@ -771,6 +771,53 @@ int lorab200_decode_dev(lorab200_ctx *c, const uint16_t *symbols_dev, size_t n_p
     return LORAB200_OK;
 }
 
+size_t lorab200_encode_symbols(int sf, const lorab200_encoder_cfg *cfg, size_t payload_length)
+{
+    if (!cfg || sf < 7 || sf > 12 || cfg->rdd < 0 || cfg->rdd > 4 || payload_length > 255) return 0;
+    const int ppm = cfg->ppm ? cfg->ppm : sf;
+    if (ppm < 5 || ppm > sf) return 0;
+    EncoderCfg e{sf, cfg->ppm, cfg->rdd, cfg->explicit_header, cfg->crc, cfg->whitening};
+    return codec_enc_symbols(e, unsigned(payload_length));
+}
+
+int lorab200_encode_dev(lorab200_ctx *c, const uint8_t *payloads_dev, size_t n_packets, size_t payload_stride,
+                        const int32_t *lengths_dev, const lorab200_encoder_cfg *cfg, uint16_t *symbols_dev,
+                        size_t symbols_stride, int32_t *n_symbols_dev, void *cuda_stream)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    c->err.clear();
+    if (n_packets == 0) return LORAB200_OK;
+    if (!payloads_dev || !cfg || !symbols_dev || !n_symbols_dev) return fail(c, LORAB200_ERR_INVALID, "null pointer");
+    if (cfg->rdd < 0 || cfg->rdd > 4) return fail(c, LORAB200_ERR_INVALID, "rdd must be 0..4");
+    const int ppm = cfg->ppm ? cfg->ppm : c->sf;
+    if (ppm < 5 || ppm > c->sf) return fail(c, LORAB200_ERR_INVALID, "ppm must be 0 or 5..SF (LoRaEncoder.cpp:176-177)");
+    if (payload_stride == 0 || payload_stride > 255) return fail(c, LORAB200_ERR_INVALID, "payload_stride must be 1..255 (the header length field is one byte)");
+    if (symbols_stride == 0 || symbols_stride > 65535) return fail(c, LORAB200_ERR_INVALID, "symbols_stride out of range");
+    CU_TRY(c, cudaSetDevice(c->device));
+    EncodeParams p{};
+    p.payloads = payloads_dev;
+    p.n_packets = n_packets;
+    p.payload_stride = unsigned(payload_stride);
+    p.lengths = lengths_dev;
+    p.cfg = EncoderCfg{c->sf, cfg->ppm, cfg->rdd, cfg->explicit_header, cfg->crc, cfg->whitening};
+    p.symbols = symbols_dev;
+    p.sym_stride = unsigned(symbols_stride);
+    p.n_symbols = n_symbols_dev;
+    p.max_bytes = p.payload_stride + 2;
+    p.max_cw = codec_enc_codewords(p.cfg, p.payload_stride);
+    int st;
+    const size_t bytes_total = (size_t(p.max_bytes) * n_packets + 15) & ~size_t(15);
+    if ((st = ensure_dev(c, c->d_dec_scratch, bytes_total + size_t(p.max_cw) * n_packets))) return st;
+    p.byte_scratch = static_cast<uint8_t *>(c->d_dec_scratch.p);
+    p.cw_scratch = p.byte_scratch + bytes_total;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    encode_kernel<<<unsigned((n_packets + 63) / 64), 64, 0, s>>>(p);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    c->last_kernel = "encode";
+    return LORAB200_OK;
+}
+
 size_t lorab200_mod_samples(int sf, int ovs, size_t syms_per_packet, size_t padding)
 {
     if (sf < 7 || sf > 12 || ovs < 1 || ovs > 256) return 0;

@@ -20,3 +20,14 @@ extern "C" int codec_host_decode(const int32_t *cfg8 /* sf, ppm, rdd, explicit, 
     std::vector<uint8_t> cw(lorab200::codec_num_codewords(c, n) + 16), bytes(cw.size() / 2 + 16);
     return lorab200::decode_packet(c, sym.data(), n, cw.data(), bytes.data(), out, unsigned(out_cap));
 }
+
+extern "C" int codec_host_encode(const int32_t *cfg6 /* sf, ppm, rdd, explicit, crc, whitening */,
+                                 const uint8_t *payload, int length, uint16_t *symbols, int max_symbols)
+{
+    lorab200::EncoderCfg c;
+    c.sf = cfg6[0]; c.ppm = cfg6[1]; c.rdd = cfg6[2]; c.explicit_hdr = cfg6[3]; c.crc = cfg6[4]; c.whitening = cfg6[5];
+    const unsigned n = unsigned(length);
+    if (int(lorab200::codec_enc_symbols(c, n)) > max_symbols) return -1;
+    std::vector<uint8_t> bytes(n + 2), cw(lorab200::codec_enc_codewords(c, n));
+    return lorab200::encode_packet(c, payload, n, bytes.data(), cw.data(), symbols);
+}

@@ -216,6 +216,45 @@ int loopback_encode(const LoopCfg *cfg, const unsigned char *payload, int length
     }
 }
 
+/* Encoder with every setter: cfg6 = sf, ppm, rdd, explicit, crc, whitening. */
+int loopback_encode_cfg(const int *cfg6, const unsigned char *payload, int length,
+                        unsigned short *syms_out, int max_syms, int *n_syms, char *err256)
+{
+    try
+    {
+        static const char *crs[] = {"4/4", "4/5", "4/6", "4/7", "4/8"};
+        std::unique_ptr<Pothos::Block> encoder(Pothos::BlockRegistry::make("/lora/lora_encoder"));
+        encoder->call("setSpreadFactor", size_t(cfg6[0]));
+        encoder->call("setSymbolSize", size_t(cfg6[1]));
+        encoder->call("setCodingRate", std::string(crs[cfg6[2]]));
+        encoder->call("enableExplicit", bool(cfg6[3] != 0));
+        encoder->call("enableCrc", bool(cfg6[4] != 0));
+        encoder->call("enableWhitening", bool(cfg6[5] != 0));
+        ministream::Topology topology;
+        encoder->output("0")->collect = true;
+        topology.add(encoder.get());
+        topology.commit();
+        Pothos::Packet pkt;
+        pkt.payload = Pothos::BufferChunk(typeid(uint8_t), size_t(length));
+        std::memcpy(pkt.payload.as<void *>(), payload, size_t(length));
+        ministream::Topology::feedMessage(encoder.get(), "0", Pothos::Object(pkt));
+        topology.run();
+        const auto &msgs = encoder->output("0")->collectedMessages;
+        if (msgs.size() != 1) throw Pothos::Exception("loopback_encode_cfg", "encoder produced no packet");
+        const auto &out = msgs[0].extract<Pothos::Packet>();
+        const int n = int(out.payload.length / 2);
+        if (n > max_syms) throw Pothos::Exception("loopback_encode_cfg", "syms_out too small");
+        std::memcpy(syms_out, out.payload.as<const void *>(), size_t(n) * 2);
+        *n_syms = n;
+        return 0;
+    }
+    catch (const std::exception &ex)
+    {
+        std::strncpy(err256, ex.what(), 255);
+        return -1;
+    }
+}
+
 /* Modulator only: one packet of symbols -> IQ, by the reference LoRaMod (LoRaMod.cpp, ovs = 1). */
 int loopback_mod(const LoopCfg *cfg, const unsigned short *syms, int n_syms,
                  float *iq_out, unsigned long long max_samples, unsigned long long *n_samples, char *err256)

@@ -35,6 +35,7 @@ def _lib():
     L.loopback_rx.argtypes = [C.POINTER(LoopCfg), C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.POINTER(LoopOut)]
     L.loopback_encode.argtypes = [C.POINTER(LoopCfg), C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                   C.c_char_p]
+    L.loopback_encode_cfg.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_char_p]
     L.loopback_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_char_p]
     L.loopback_mod.argtypes = [C.POINTER(LoopCfg), C.c_void_p, C.c_int, C.c_void_p, C.c_ulonglong,
                                C.POINTER(C.c_ulonglong), C.c_char_p]
@@ -49,6 +50,18 @@ def encode(sf, cr, payload):
     n = C.c_int()
     err = C.create_string_buffer(256)
     if L.loopback_encode(C.byref(cfg), payload, len(payload), syms.ctypes.data_as(C.c_void_p), syms.size, C.byref(n), err):
+        raise RuntimeError(err.value.decode())
+    return syms[: n.value].copy()
+
+
+def encode_cfg(cfg6, payload):
+    """payload -> symbols by the reference LoRaEncoder; cfg6 = (sf, ppm, rdd, explicit, crc, whitening)."""
+    L = _lib()
+    cfg = (C.c_int * 6)(*[int(v) for v in cfg6])
+    syms = np.empty(4096, np.uint16)
+    n = C.c_int()
+    err = C.create_string_buffer(256)
+    if L.loopback_encode_cfg(cfg, payload, len(payload), syms.ctypes.data_as(C.c_void_p), syms.size, C.byref(n), err):
         raise RuntimeError(err.value.decode())
     return syms[: n.value].copy()
 

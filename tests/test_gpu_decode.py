@@ -97,3 +97,63 @@ def test_whole_receive_chain_on_the_device(lib, cuda_ok, sf):
         assert lens[i] == ref_len and bytes(out[i, : lens[i]]) == ref
         assert ref[: len(p) - 2] == p[: len(p) - 2]
     d.close()
+
+
+@needs_chain
+@pytest.mark.parametrize("sf,ppm,rdd,explicit,crc,whitening", [
+    (7, 0, 4, 1, 1, 1), (8, 0, 1, 1, 0, 1), (9, 7, 2, 0, 1, 1), (10, 0, 3, 1, 1, 0), (12, 10, 0, 1, 1, 1), (12, 0, 4, 0, 0, 1)])
+def test_encode_dev_matches_reference_encoder(lib, cuda_ok, sf, ppm, rdd, explicit, crc, whitening):
+    """lorab200_encode_dev against the unmodified LoRaEncoder.cpp: exact-fit payload lengths bit for bit,
+    other lengths on every padding-free block (tests/test_codec.py explains the reference's padding)."""
+    import torch
+    rng = np.random.default_rng(sf + rdd)
+    P = ppm or sf
+    lens = np.array([1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233] + list(range(4, 40)), np.int32)
+    stride = int(lens.max())
+    host = rng.integers(0, 256, (lens.size, stride), dtype=np.uint8)
+    d = lib.Demod(sf)
+    syms, nsy = d.encode_dev(torch.from_numpy(host).cuda(), torch.from_numpy(lens).cuda(), ppm=ppm, rdd=rdd,
+                             explicit_header=bool(explicit), crc=bool(crc), whitening=bool(whitening))
+    assert d.last_kernel == "encode"
+    syms, nsy = syms.cpu().numpy().view(np.uint16), nsy.cpu().numpy()
+    exact = 0
+    for i, ln in enumerate(lens):
+        ref = loopback.encode_cfg((sf, ppm, rdd, explicit, crc, whitening), bytes(host[i, :ln]))
+        assert nsy[i] == ref.size
+        n_nib = (int(ln) + 2 * crc) * 2 + 5 * explicit
+        if n_nib % P == 0:
+            assert np.array_equal(syms[i, : ref.size], ref), (i, ln)
+            exact += 1
+        else:
+            full = n_nib // P
+            keep = 8 + max(0, full - 1) * (4 + rdd) if full >= 1 else 0
+            assert np.array_equal(syms[i, :keep], ref[:keep]), (i, ln)
+    assert exact >= 2
+    d.close()
+
+
+@needs_chain
+def test_transmit_and_receive_chains_on_the_device(lib, cuda_ok):
+    """bytes -> encode_dev -> mod_dev -> rx_dev -> decode_dev -> bytes, four launches, no reference code in
+    the loop; the reference receiver decodes the same frames to the same bytes."""
+    import torch
+    sf, nch, ln = 8, 6, 17
+    rng = np.random.default_rng(8)
+    payloads = rng.integers(0, 256, (nch, ln), dtype=np.uint8)
+    d = lib.Demod(sf)
+    syms, nsy = d.encode_dev(torch.from_numpy(payloads).cuda(), rdd=4, crc=True)
+    assert int(nsy.min()) == int(nsy.max()) == syms.shape[1]
+    iq = d.mod_dev(syms, padding=140, ampl=1.0, mode=lib.MOD_IDEAL)
+    iq = iq + 0.02 * torch.view_as_complex(torch.randn((*iq.shape, 2), device=iq.device, generator=torch.Generator("cuda").manual_seed(1)))
+    r = d.rx_dev(iq.contiguous(), mtu=128, max_packets=4)
+    lens = r["info"][:, :, 0].contiguous().reshape(-1)
+    out, blen = d.decode_dev(r["symbols"].reshape(nch * 4, 128), lens, rdd=4)
+    torch.cuda.synchronize()
+    out, blen, npk = out.cpu().numpy(), blen.cpu().numpy(), r["n_packets"].cpu().numpy()
+    host_iq = iq.cpu().numpy()
+    for c in range(nch):
+        assert npk[c] == 1
+        assert bytes(out[c * 4, :ln]) == bytes(payloads[c])
+        ref = loopback.receive(sf, 4, host_iq[c], use_b200=False, debug_ports=True, mtu=128)
+        assert ref["decoded"] and ref["decoded"][0][:ln] == bytes(payloads[c])
+    d.close()
