@@ -31,3 +31,27 @@ extern "C" int codec_host_encode(const int32_t *cfg6 /* sf, ppm, rdd, explicit, 
     std::vector<uint8_t> bytes(n + 2), cw(lorab200::codec_enc_codewords(c, n));
     return lorab200::encode_packet(c, payload, n, bytes.data(), cw.data(), symbols);
 }
+
+/* ---- the receiver state machine (lora-sdr_b200/csrc/rx_fsm.h), host build, for tests ---------- */
+#include "../lora-sdr_b200/csrc/rx_fsm.h"
+
+extern "C" int rx_host_needs_second(const int32_t *cfg4 /* n, sync, mtu, thresh as float bits */, const void *state,
+                                    const lorab200_result *r0)
+{
+    lorab200::RxCfg c;
+    c.n = cfg4[0]; c.sync = cfg4[1]; c.mtu = cfg4[2];
+    std::memcpy(&c.thresh, &cfg4[3], 4);
+    return lorab200::rx_needs_second(c, *static_cast<const lorab200::RxState *>(state), *r0) ? 1 : 0;
+}
+
+/* returns consume | emit_symbol | post_packet through out3 */
+extern "C" void rx_host_step(const int32_t *cfg4, void *state, const lorab200_result *r0, int idx_after0, int have_r1,
+                             const lorab200_result *r1, int64_t *out3)
+{
+    lorab200::RxCfg c;
+    c.n = cfg4[0]; c.sync = cfg4[1]; c.mtu = cfg4[2];
+    std::memcpy(&c.thresh, &cfg4[3], 4);
+    const lorab200::RxAction a = lorab200::rx_step(c, *static_cast<lorab200::RxState *>(state), *r0, idx_after0,
+                                                   have_r1 != 0, *r1);
+    out3[0] = a.consume; out3[1] = a.emit_symbol; out3[2] = a.post_packet;
+}
