@@ -128,7 +128,8 @@ def test_encode_dev_matches_reference_encoder(lib, cuda_ok, sf, ppm, rdd, explic
             full = n_nib // P
             keep = 8 + max(0, full - 1) * (4 + rdd) if full >= 1 else 0
             assert np.array_equal(syms[i, :keep], ref[:keep]), (i, ln)
-    assert exact >= 2
+    fits = sum(((int(ln) + 2 * crc) * 2 + 5 * explicit) % P == 0 for ln in lens)
+    assert exact == fits               # (an odd nibble count never fills blocks of an even PPM)
     d.close()
 
 
