@@ -44,6 +44,10 @@ struct DemodParams {
     float2 *fft;              // optional [W][N]
     float2 *dec;              // optional [W][N]
     unsigned int early_iq;    // LORAB200_FLAG_INPUT_STABLE: IQ may be prefetched before the prior grid drains
+    // FINE_WALK fast path (fine_walk.h): inside the region where every step of the recurrence is the
+    // same integer fine_lin_step, a thread's 16 indices are x - i*step; valid while the indices stay in
+    // [fine_lin_lo, fine_len).  fine_lin_ok == 0: always walk the recurrence literally.
+    int fine_lin_ok, fine_lin_step, fine_lin_lo;
     unsigned int seg_windows; // multi-segment batches (lorab200_demod_multi_dev): windows per segment, else 0
 };
 

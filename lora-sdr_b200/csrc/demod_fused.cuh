@@ -438,11 +438,21 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
                 int x = live ? __ldg(p.fine_x16 + size_t(w) * G + t) : 0;
                 const uint32_t fx = xbase + uint32_t(wsub) * C::FINE_WSTRIDE * 4u; // this window's index area
                 const uint32_t cbase = fx + uint32_t(fine_pad_dyn(16 * t)) * 4u;
+                // Almost every chunk lies inside one region of the recurrence, where each step subtracts
+                // the same integer (fine_walk.h): then the 16 indices are an arithmetic progression.
+                // Chunks that touch a region boundary or the wrap walk the recurrence literally.
+                const int xe = x - 15 * p.fine_lin_step;
+                const bool linear = p.fine_lin_ok && min(x, xe) >= p.fine_lin_lo && max(x, xe) < p.fine_len;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     int v[4];
+                    if (linear) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { v[i] = x; x = fine_next(x, p.fine_step, p.fine_len); }
+                        for (int i = 0; i < 4; ++i) v[i] = x - (4 * q + i) * p.fine_lin_step;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { v[i] = x; x = fine_next(x, p.fine_step, p.fine_len); }
+                    }
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + q * 16u),
                                  "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
                 }

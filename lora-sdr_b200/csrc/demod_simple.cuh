@@ -32,6 +32,23 @@ __device__ __forceinline__ int kiss_input_index(int j)
     return i;
 }
 
+// The inverse map: input sample i lands in slot j (i's base-4 digits, least significant first,
+// are j's digits most significant first; the top bit of i is j's last bit when SF is odd).
+template <int SF>
+__device__ __forceinline__ int kiss_output_slot(int i)
+{
+    constexpr int L4 = SF / 2;
+    int j = 0;
+    int shift = SF;
+#pragma unroll
+    for (int s = 0; s < L4; ++s) {
+        shift -= 2;
+        j |= ((i >> (2 * s)) & 3) << shift;
+    }
+    if (SF & 1) j |= (i >> (2 * L4)) & 1;
+    return j;
+}
+
 constexpr int kSimpleThreads = 128;
 
 // One window, cooperatively by a CTA of kSimpleThreads threads: dechirp (+ optional fine-tune
@@ -49,13 +66,12 @@ __device__ __forceinline__ RawResult simple_window(const float2 *__restrict__ in
     constexpr int T = kSimpleThreads;
     const int tid = threadIdx.x;
 
-    // dechirp + digit-reversed load
-    for (int j = tid; j < N; j += T) {
-        const int i = kiss_input_index<SF>(j);
+    // dechirp in input order (coalesced global reads), scatter into kissfft's digit-reversed slots
+    for (int i = tid; i < N; i += T) {
         float2 d = cx_mul(in[i], chirp[i]);
         if (fine) d = cx_mul(d, fine[walk ? fidx[i] : idx_const]);
         if (dec_out) dec_out[i] = d;
-        F[j] = d;
+        F[kiss_output_slot<SF>(i)] = d;
     }
 
     // stages, deepest first: radix-2 (odd SF) with m=1, then radix-4 with m=..,

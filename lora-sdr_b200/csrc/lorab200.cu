@@ -7,6 +7,7 @@
 
 #include <cstdio>
 #include <cmath>
+#include <limits>
 #include <cstring>
 #include <new>
 #include <atomic>
@@ -414,7 +415,14 @@ int run_demod(lorab200_ctx *c, const void *iq_dev, size_t n_windows, size_t stri
         int st = fine_prefix(c, fine->index, fine->step, p.fine_len, n_windows, s);
         if (st) return st;
         p.fine_x16 = static_cast<const int32_t *>(c->d_fine_x.p);
-        fine->index = FineWalk(p.fine_len, fine->step).advance(fine->index, uint64_t(n_windows) * c->n);
+        const FineWalk fwalk(p.fine_len, fine->step);
+        fine->index = fwalk.advance(fine->index, uint64_t(n_windows) * c->n);
+        // arithmetic-progression fast path of the kernel: an integer step d, or (rounding never carries,
+        // Kp == none) every state with k = x - D >= 1 steps by D + 1
+        const bool kp_none = fwalk.Kp == std::numeric_limits<int64_t>::max();
+        p.fine_lin_ok = (fwalk.integer || kp_none) ? 1 : 0;
+        p.fine_lin_step = int(fwalk.integer ? fwalk.D : fwalk.D + 1);
+        p.fine_lin_lo = fwalk.integer ? 0 : int(fwalk.D + 1 > 0 ? fwalk.D + 1 : 0);
     }
 
     cudaError_t e;
