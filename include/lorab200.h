@@ -215,7 +215,7 @@ void lorab200_pack_symbols(const lorab200_result *results, size_t n, int16_t *sy
  * Batched modulator: n_packets packets of syms_per_packet symbols each (uint16, DEVICE
  * memory, as the reference encoder emits them) -> complex64 IQ in DEVICE memory, framed
  * as LoRaMod.cpp:120-229 does: 10 preamble up-chirps, the two sync-word chirps, two
- * down-chirps and a quarter down-chirp, the data symbols, `padding` symbols of zeros.
+ * down-chirps and a quarter down-chirp, the data symbols, max(padding, 1) symbols of zeros.
  * Packet p occupies iq_dev[p * lorab200_mod_samples(...) ...].  Replaces /lora/lora_mod
  * (LoRaMod.cpp:280-281; setSync, setPadding, setAmplitude, setOvs are the arguments).
  *

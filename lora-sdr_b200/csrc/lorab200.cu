@@ -829,7 +829,8 @@ int lorab200_encode_dev(lorab200_ctx *c, const uint8_t *payloads_dev, size_t n_p
 size_t lorab200_mod_samples(int sf, int ovs, size_t syms_per_packet, size_t padding)
 {
     if (sf < 7 || sf > 12 || ovs < 1 || ovs > 256) return 0;
-    return size_t(mod_samples_per_packet(1u << sf, unsigned(ovs), unsigned(syms_per_packet), unsigned(padding)));
+    // LoRaMod.cpp:222-229: the padding state always emits at least one zero symbol
+    return size_t(mod_samples_per_packet(1u << sf, unsigned(ovs), unsigned(syms_per_packet), unsigned(padding ? padding : 1)));
 }
 
 int lorab200_mod_dev(lorab200_ctx *c, const uint16_t *symbols_dev, size_t n_packets, size_t syms_per_packet,
@@ -851,7 +852,7 @@ int lorab200_mod_dev(lorab200_ctx *c, const uint16_t *symbols_dev, size_t n_pack
     p.symbols = symbols_dev;
     p.n_packets = n_packets;
     p.n_syms = unsigned(syms_per_packet);
-    p.padding = unsigned(padding);
+    p.padding = unsigned(padding ? padding : 1);   // LoRaMod.cpp:222-229: at least one zero symbol
     p.sync = sync;
     p.ovs = unsigned(ovs);
     p.n = unsigned(c->n);

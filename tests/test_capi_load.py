@@ -88,3 +88,24 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only",
                         f"-I{ROOT / 'include'}", str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_size_helpers_match_the_reference_blocks(lib):
+    """lorab200_encode_symbols / lorab200_mod_samples are pure host functions (no context, no GPU):
+    they must agree with what the unmodified reference encoder and modulator produce."""
+    import ctypes as C
+    import numpy as np
+    import loopback
+    if not loopback.available():
+        pytest.skip("oracle/_ref/libloraloop.so not built")
+    L = lib.load_library()
+    rng = np.random.default_rng(0)
+    for sf, rdd, ex, crc in ((7, 4, 1, 1), (9, 1, 1, 0), (12, 3, 0, 1), (10, 0, 0, 0)):
+        cfg = (C.c_int32 * 5)(0, rdd, ex, crc, 1)
+        for ln in (1, 7, 20, 100, 255):
+            ref = loopback.encode_cfg((sf, 0, rdd, ex, crc, 1), bytes(rng.integers(0, 256, ln, dtype=np.uint8)))
+            assert L.lorab200_encode_symbols(sf, C.cast(cfg, C.c_void_p), ln) == ref.size
+    for sf, nsy, pad in ((7, 12, 3), (10, 40, 1), (12, 8, 0)):
+        ref = loopback.modulate(sf, np.zeros(nsy, np.uint16), padding=pad)
+        assert L.lorab200_mod_samples(sf, 1, nsy, pad) == ref.size
+    assert L.lorab200_mod_samples(6, 1, 4, 1) == 0 and L.lorab200_mod_samples(7, 0, 4, 1) == 0
