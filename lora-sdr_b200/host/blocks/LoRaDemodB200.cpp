@@ -15,9 +15,11 @@
 //   * everything else (preamble re-timing `total = N - value`, sync word, down-chirps,
 //     quarter chirp) depends on the previous result and is done one window at a time.
 //
-// The state machine itself stays on the host and is a restatement of LoRaDemod.cpp:173-312,
-// including its quirks (the sync-word look-ahead overwrites power/powerAvg/fIndex; the
-// quarter-chirp skip uses integer halving).  Differences, all deliberate:
+// The state machine stays on the host: it is the transition function of csrc/rx_fsm.h
+// (rx_needs_second / rx_step, the restatement of LoRaDemod.cpp:173-327 that the on-device
+// receiver lorab200_rx_dev runs per channel too), so the block and the device receiver cannot
+// drift apart.  This file adds what a Pothos block owns around it: ports, packets, labels,
+// signals, and the batching of GPU calls.  Differences from the reference, all deliberate:
 //   * _finefreqError, _prevValue, _freqError, _symCount are zero-initialised (the reference
 //     reads _finefreqError uninitialised, LoRaDemod.cpp:160 / :386-392);
 //   * work() may consume many windows per call; debug ports then carry the concatenation
@@ -38,6 +40,7 @@
 #include <vector>
 
 #include "../../../include/lorab200.h"
+#include "../../csrc/rx_fsm.h"
 
 #ifndef LORAB200_REGISTRY_PATH
 #define LORAB200_REGISTRY_PATH "/lora/lora_demod"
@@ -96,15 +99,9 @@ public:
         _thresh(-30.0f),
         _mtu(256),
         _debugPorts(true),
-        _maxBatch(4096),
-        _state(STATE_FRAMESYNC),
-        _table(LORAB200_TABLE_UP),
-        _symCount(0),
-        _prevValue(0),
-        _freqError(0),
-        _fineTuneIndex(0),
-        _finefreqError(0.0f)
+        _maxBatch(4096)
     {
+        lorab200::rx_reset(_st);
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, setSync));
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, setThreshold));
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, setMTU));
@@ -161,13 +158,7 @@ public:
 
     void activate(void)
     {
-        _state = STATE_FRAMESYNC;
-        _table = LORAB200_TABLE_UP;
-        _symCount = 0;
-        _prevValue = 0;
-        _freqError = 0;
-        _fineTuneIndex = 0;
-        _finefreqError = 0.0f;
+        lorab200::rx_reset(_st);
     }
 
     void work(void)
@@ -193,134 +184,67 @@ public:
         size_t fftOut = 0;    //elements produced on the fft port in this call
         _cache.count = 0;
 
+        lorab200::RxCfg cfg;
+        cfg.n = int(N); cfg.sync = int(_sync); cfg.thresh = _thresh; cfg.mtu = int(_mtu);
+
         while (avail - off >= N*2 and rawRoom - off >= N*2 and fftRoom - fftOut >= N)
         {
+            //the window at the current offset, and -- when it looks like the first sync word -- the next one
             const Window &win = this->demodAt(inBuff, avail, off, 0);
-            const size_t value = size_t(win.res.index);
-            float power = win.res.power;
-            float powerAvg = win.res.power_avg;
-            float fIndex = win.res.f_index;
-            const float snr = power - powerAvg;
-            const bool squelched = (snr < _thresh);
-
-            //the dechirp loop advanced the fine tune index over the window (LoRaDemod.cpp:160-162)
-            const int ftAtWindowStart = _fineTuneIndex;
-            _fineTuneIndex = win.idxAfter;
-
+            const lorab200_result r0 = win.res;
+            const int idxAfter0 = win.idxAfter;
             if (_debugPorts)
             {
                 std::memcpy(decBuff + off, win.dec, N*sizeof(std::complex<float>));
                 std::memcpy(fftBuff + fftOut, win.fft, N*sizeof(std::complex<float>));
             }
+            const bool second = lorab200::rx_needs_second(cfg, _st, r0);
+            lorab200_result r1 = r0;
+            if (second)
+            {
+                //demodAt continues the fine tune walk from where the first window left it
+                _st.fine_index = idxAfter0;
+                const Window &win1 = this->demodAt(inBuff, avail, off, 1);
+                r1 = win1.res;
+                if (_debugPorts) std::memcpy(decBuff + off + N, win1.dec, N*sizeof(std::complex<float>));
+            }
 
-            size_t total = 0;
+            const int before = _st.phase;
+            const bool squelched = (r0.power - r0.power_avg) < _thresh;
+            const lorab200::RxAction act = lorab200::rx_step(cfg, _st, r0, idxAfter0, second, r1);
+            const size_t total = act.consume;
+
+            //what the block owns around a transition: the packet, the signals, the labels
             std::string id;
-            switch (_state)
+            switch (before)
             {
-            ////////////////////////////////////////////////////////////////
-            case STATE_FRAMESYNC:
-            ////////////////////////////////////////////////////////////////
-            {
-                //format as observed from inspecting RN2483 (LoRaDemod.cpp:183-185)
-                const bool syncd = not squelched and (_prevValue+4)/8 == 0;
-                const bool match0 = (value+4)/8 == unsigned(_sync>>4);
-                bool match1 = false;
-
-                //the look-ahead window continues the fine tune walk from where the first
-                //window left it, on a copy (LoRaDemod.cpp:191-203); its detect() call
-                //overwrites power, powerAvg and fIndex
-                if (syncd and match0)
-                {
-                    (void)ftAtWindowStart;
-                    const Window &win1 = this->demodAt(inBuff, avail, off, 1);
-                    power = win1.res.power;
-                    powerAvg = win1.res.power_avg;
-                    fIndex = win1.res.f_index;
-                    match1 = (size_t(win1.res.index)+4)/8 == unsigned(_sync & 0xf);
-                    if (_debugPorts) std::memcpy(decBuff + off + N, win1.dec, N*sizeof(std::complex<float>));
-                }
-
-                if (syncd and match0 and match1)
-                {
-                    total = 2*N;
-                    _state = STATE_DOWNCHIRP0;
-                    _table = LORAB200_TABLE_DOWN;
-                    id = "SYNC";
-                }
-                //otherwise its a frequency error
-                else if (not squelched)
-                {
-                    total = N - value;
-                    _finefreqError += fIndex;
-                    id = "P " + fixed4(fIndex);
-                }
-                //just noise
-                else
-                {
-                    total = N;
-                    _finefreqError = 0;
-                    _fineTuneIndex = 0;
-                }
-            } break;
-
-            ////////////////////////////////////////////////////////////////
-            case STATE_DOWNCHIRP0:
-            ////////////////////////////////////////////////////////////////
-            {
-                _state = STATE_DOWNCHIRP1;
-                total = N;
+            case lorab200::RX_FRAMESYNC:
+                if (_st.phase == lorab200::RX_DOWNCHIRP0) id = "SYNC";
+                else if (not squelched) id = "P " + fixed4(second ? r1.f_index : r0.f_index);
+                break;
+            case lorab200::RX_DOWNCHIRP0:
                 id = "DC";
-                int error = int(value);
-                if (value > N/2) error -= int(N);
-                _freqError = error;
-            } break;
-
-            ////////////////////////////////////////////////////////////////
-            case STATE_DOWNCHIRP1:
-            ////////////////////////////////////////////////////////////////
-            {
-                _state = STATE_QUARTERCHIRP;
-                total = N;
-                _table = LORAB200_TABLE_UP;
+                break;
+            case lorab200::RX_DOWNCHIRP1:
                 _outSymbols = Pothos::BufferChunk(typeid(int16_t), _mtu);
-
-                int error = int(value);
-                if (value > N/2) error -= int(N);
-                _freqError = (_freqError + error)/2;
-
-                this->emitSignal("error", _freqError);
-                this->emitSignal("power", power);
-                this->emitSignal("snr", snr);
-            } break;
-
-            ////////////////////////////////////////////////////////////////
-            case STATE_QUARTERCHIRP:
-            ////////////////////////////////////////////////////////////////
-            {
-                _state = STATE_DATASYMBOLS;
-                total = N/4 + (_freqError / 2);
-                _finefreqError += (_freqError / 2);
-                _symCount = 0;
+                this->emitSignal("error", int(_st.sig_error));
+                this->emitSignal("power", _st.sig_power);
+                this->emitSignal("snr", _st.sig_snr);
+                break;
+            case lorab200::RX_QUARTERCHIRP:
                 id = "QC";
-            } break;
-
-            ////////////////////////////////////////////////////////////////
-            case STATE_DATASYMBOLS:
-            ////////////////////////////////////////////////////////////////
-            {
-                total = N;
-                _outSymbols.as<int16_t *>()[_symCount++] = int16_t(value);
-                if (_symCount >= _mtu or squelched)
+                break;
+            default: //RX_DATASYMBOLS
+                _outSymbols.as<int16_t *>()[_st.sym_count - 1] = int16_t(act.emit_symbol);
+                if (act.post_packet)
                 {
                     Pothos::Packet pkt;
                     pkt.payload = _outSymbols;
-                    pkt.payload.length = _symCount*sizeof(int16_t);
+                    pkt.payload.length = size_t(_st.sym_count)*sizeof(int16_t);
                     this->output(0)->postMessage(pkt);
-                    _finefreqError = 0;
-                    _state = STATE_FRAMESYNC;
                 }
-                id = "S" + std::to_string(_symCount) + " " + fixed4(fIndex);
-            } break;
+                id = "S" + std::to_string(_st.sym_count) + " " + fixed4(r0.f_index);
+                break;
             }
 
             if (_debugPorts)
@@ -335,7 +259,6 @@ public:
                 fftOut += N;
             }
             off += total;
-            _prevValue = short(value);
         }
 
         inPort->consume(off);
@@ -413,11 +336,11 @@ private:
     {
         Cache &c = _cache;
         const size_t at = off + ahead*N;
-        int idxHere = _fineTuneIndex;          //index at the first sample of the requested window
+        int idxHere = _st.fine_index;          //index at the first sample of the requested window
         //the look-ahead window (ahead == 1) is only asked for after _fineTuneIndex has
         //been advanced over the first window: idxHere is already right in both cases
         const bool hit = c.count > 0 and at >= c.off and (at - c.off) % N == 0 and (at - c.off)/N < c.count
-            and c.table == _table and c.ffe == _finefreqError
+            and c.table == _st.table and c.ffe == _st.ffe
             and (c.resetEach ? idxHere == 0 : this->cacheIdxAt((at - c.off)/N) == idxHere);
         if (not hit)
         {
@@ -438,27 +361,27 @@ private:
             if (ahead == 0 and fit >= 2)
             {
                 const size_t maxWin = std::min<size_t>(fit - 1, _debugPorts ? size_t(kDebugWindows) : _maxBatch);
-                if (_state == STATE_DATASYMBOLS)
+                if (_st.phase == lorab200::RX_DATASYMBOLS)
                 {
-                    count = std::min<size_t>(maxWin, std::max<size_t>(1, _mtu - _symCount));
+                    count = std::min<size_t>(maxWin, std::max<size_t>(1, _mtu - size_t(_st.sym_count)));
                 }
-                else if (_state == STATE_FRAMESYNC and _finefreqError == 0.0f and idxHere == 0)
+                else if (_st.phase == lorab200::RX_FRAMESYNC and _st.ffe == 0.0f and idxHere == 0)
                 {
                     count = std::min(maxWin, _idleSpec);  //idle: every window starts from a reset fine tune state
                     resetEach = true;
                 }
             }
-            c.off = at; c.count = count; c.table = _table; c.idx0 = idxHere; c.ffe = _finefreqError;
+            c.off = at; c.count = count; c.table = _st.table; c.idx0 = idxHere; c.ffe = _st.ffe;
             c.resetEach = resetEach;
             c.res.resize(count);
             c.idxAfter.resize(count);
             if (_debugPorts) { c.dec.resize(count*N); c.fft.resize(count*N); }
             lorab200_fine fine;
             fine.index = idxHere;
-            fine.step = _finefreqError * _fineSteps;
+            fine.step = _st.ffe * _fineSteps;
             ++_demodCalls;
             _demodWindows += count;
-            const int st = lorab200_demod_host(_ctx, reinterpret_cast<const float *>(in + at), count, N, _table, &fine,
+            const int st = lorab200_demod_host(_ctx, reinterpret_cast<const float *>(in + at), count, N, _st.table, &fine,
                 c.res.data(), _debugPorts ? reinterpret_cast<float *>(c.fft.data()) : nullptr,
                 _debugPorts ? reinterpret_cast<float *>(c.dec.data()) : nullptr);
             if (st != LORAB200_OK)
@@ -468,7 +391,7 @@ private:
             int idx = idxHere;
             for (size_t k = 0; k < count; k++)
             {
-                idx = resetEach ? 0 : this->rollIndex(idx, _finefreqError);
+                idx = resetEach ? 0 : this->rollIndex(idx, _st.ffe);
                 c.idxAfter[k] = idx;
             }
         }
@@ -510,23 +433,9 @@ private:
     Pothos::OutputPort *_decPort;
     Pothos::OutputPort *_fftPort;
 
-    //state
-    enum LoraDemodState
-    {
-        STATE_FRAMESYNC,
-        STATE_DOWNCHIRP0,
-        STATE_DOWNCHIRP1,
-        STATE_QUARTERCHIRP,
-        STATE_DATASYMBOLS,
-    };
-    LoraDemodState _state;
-    int _table;
-    size_t _symCount;
+    //state: the reference block's private members (LoRaDemod.cpp:362-392) as one struct, plus the packet
+    lorab200::RxState _st;
     Pothos::BufferChunk _outSymbols;
-    short _prevValue;
-    int _freqError;
-    int _fineTuneIndex;
-    float _finefreqError;
 };
 
 static Pothos::BlockRegistry registerLoRaDemodB200(
