@@ -30,22 +30,12 @@ RESULT_DTYPE = np.dtype(
 
 
 def build(force: bool = False) -> None:
-    """Compile the restatement and (when /root/reference exists) the real reference."""
-    src_newer = (not LIB_ORACLE.exists()) or any(
-        (HERE / f).stat().st_mtime > LIB_ORACLE.stat().st_mtime
-        for f in ("lora_oracle.c", "lora_oracle.h")
-    )
-    lib_loop = HERE / "_ref" / "libloraloop.so"
-    product = HERE.parent / "lora-sdr_b200" / "liblorab200.so"
-    need_ref = Path("/root/reference").is_dir() and (
-        not LIB_REF.exists()
-        or (HERE / "ref_shim.cpp").stat().st_mtime > LIB_REF.stat().st_mtime
-        or (product.exists() and not lib_loop.exists())
-        or (lib_loop.exists() and (HERE / "loopback_driver.cpp").stat().st_mtime > lib_loop.stat().st_mtime)
-    )
-    if force or src_newer or need_ref:
-        args = ["make", "-C", str(HERE)] + (["-B"] if force else [])
-        subprocess.run(args, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    """Compile the restatement, the host build of the product's codec / state-machine headers and
+    (when /root/reference exists) the real reference + loopback chain.  Always delegates to make,
+    which knows every dependency (block shell, ministream headers, product headers); an
+    up-to-date tree costs a few milliseconds."""
+    args = ["make", "-C", str(HERE)] + (["-B"] if force else [])
+    subprocess.run(args, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
 
 
 class _Plan(C.Structure):
