@@ -157,6 +157,7 @@ struct lorab200_ctx {
     bool fine_t_valid = false;
     float fine_t_step = 0.0f;
     cudaEvent_t fine_done = nullptr;          // last kernel that read the fine scratch
+    cudaEvent_t aux_done = nullptr;           // last kernel that used the modulator / codec scratch
 };
 
 namespace {
@@ -313,6 +314,18 @@ cudaError_t launch_simple_multi(int sf, const DemodParams &p, const SegList<true
     case 12: return launch_simple_sf<12, true>(p, s, sm_count, segs);
     default: return cudaErrorInvalidValue;
     }
+}
+
+// Per-context scratch (modulator phases, codec buffers) may still be in use by the previous call
+// on another stream: order this stream after it / mark the end of this use.  (Not while `s` is
+// being captured into a graph: a capture orders its own nodes.)
+cudaError_t aux_scratch_acquire(lorab200_ctx *c, cudaStream_t s)
+{
+    return stream_capturing(s) ? cudaSuccess : cudaStreamWaitEvent(s, c->aux_done, 0);
+}
+cudaError_t aux_scratch_release(lorab200_ctx *c, cudaStream_t s)
+{
+    return stream_capturing(s) ? cudaSuccess : cudaEventRecord(c->aux_done, s);
 }
 
 // Walking fine-tune index (LoRaDemod.cpp:160-162): state at every 16th dechirped sample of
@@ -503,6 +516,7 @@ int lorab200_create(lorab200_ctx **out, int device, int sf, uint32_t flags)
         for (auto &ev : c->chunk_done)
             if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) break;
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fine_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->aux_done, cudaEventDisableTiming);
         for (auto &ev : c->ring_free)
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
         if (e != cudaSuccess) { st = fail(nullptr, LORAB200_ERR_CUDA, "cudaEventCreate", e); break; }
@@ -529,6 +543,7 @@ void lorab200_destroy(lorab200_ctx *c)
     for (auto &t : c->d_table) if (t) cudaFree(t);
     for (DevBuf *b : {&c->d_iq, &c->d_raw, &c->d_fft, &c->d_dec, &c->d_fine_t, &c->d_fine_p[0], &c->d_fine_p[1], &c->d_fine_x, &c->d_mod_phase, &c->d_mod_phasor, &c->d_dec_scratch}) if (b->p) cudaFree(b->p);
     if (c->fine_done) cudaEventDestroy(c->fine_done);
+    if (c->aux_done) cudaEventDestroy(c->aux_done);
     if (c->h_raw) cudaFreeHost(c->h_raw);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_ring) cudaFreeHost(c->h_ring);
@@ -772,8 +787,10 @@ int lorab200_decode_dev(lorab200_ctx *c, const uint16_t *symbols_dev, size_t n_p
     p.cw_scratch = reinterpret_cast<uint8_t *>(base + sym_bytes);
     p.byte_scratch = reinterpret_cast<uint8_t *>(base + sym_bytes + cw_bytes);
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    CU_TRY(c, aux_scratch_acquire(c, s));
     decode_kernel<<<unsigned((n_packets + 63) / 64), 64, 0, s>>>(p);
     CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, aux_scratch_release(c, s));
     c->launches++;
     c->last_kernel = "decode";
     return LORAB200_OK;
@@ -819,8 +836,10 @@ int lorab200_encode_dev(lorab200_ctx *c, const uint8_t *payloads_dev, size_t n_p
     p.byte_scratch = static_cast<uint8_t *>(c->d_dec_scratch.p);
     p.cw_scratch = p.byte_scratch + bytes_total;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    CU_TRY(c, aux_scratch_acquire(c, s));
     encode_kernel<<<unsigned((n_packets + 63) / 64), 64, 0, s>>>(p);
     CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, aux_scratch_release(c, s));
     c->launches++;
     c->last_kernel = "encode";
     return LORAB200_OK;
@@ -890,10 +909,12 @@ int lorab200_mod_dev(lorab200_ctx *c, const uint16_t *symbols_dev, size_t n_pack
     }
     if ((st = ensure_dev(c, c->d_mod_phase, total * sizeof(float)))) return st;
     p.phase = static_cast<float *>(c->d_mod_phase.p);
+    CU_TRY(c, aux_scratch_acquire(c, s));
     mod_phase_kernel<<<unsigned((n_packets + 31) / 32), 32, 0, s>>>(p);
     CU_TRY(c, cudaGetLastError());
     mod_polar_kernel<<<blocks(total), 256, 0, s>>>(p);
     CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, aux_scratch_release(c, s));
     c->launches += 2;
     c->last_kernel = "mod_reference";
     return LORAB200_OK;
