@@ -153,3 +153,43 @@ def test_encoder_matches_reference_encoder():
                 assert np.array_equal(host_encode(L, cfg, payload), loopback.encode_cfg(cfg, payload))
                 exact += 1
     assert exact > 100 and padded > 500
+
+
+def test_codec_round_trip_and_single_error_correction():
+    """Size-independent properties of the product codec (host build, no reference needed):
+    decode(encode(p)) == p for every configuration, and with coding rates 4/7 and 4/8 any single
+    corrupted bit per interleaver block is corrected (one symbol bit lands in exactly one codeword)."""
+    L = host_codec()
+    rng = np.random.default_rng(12345)
+    for trial in range(400):
+        sf = int(rng.integers(7, 13))
+        ppm = int(rng.choice([0, sf - 1, sf - 2]))
+        rdd = int(rng.integers(0, 5))
+        crc = int(rng.integers(0, 2))
+        wh = int(rng.integers(0, 2))
+        ln = int(rng.integers(2, 80))
+        payload = bytes(rng.integers(0, 256, ln, dtype=np.uint8))
+        syms = host_encode(L, (sf, ppm, rdd, 1, crc, wh), payload)
+        if not wh:
+            continue                                        # the decoder always de-whitens (LoRaDecoder.cpp:229-258)
+        dec_cfg = (sf, ppm, rdd, 1, 0, 8, crc, 1)           # error check on: a bad parity would drop the packet
+        n, out = host_decode(L, dec_cfg, syms)
+        want = payload if crc else payload[: ln - 2]        # (hdr off trims 5 bytes either way, see codec.h)
+        assert n == len(want) and out == want, (sf, ppm, rdd, crc, ln)
+        if rdd >= 3:
+            bad = syms.copy()
+            P = ppm or sf
+            shift = sf - P
+            # one flipped (significant) bit in one symbol of every block
+            blocks = [(0, 8)] + [(8 + b * (4 + rdd), 4 + rdd) for b in range((syms.size - 8) // (4 + rdd))]
+            for start, count in blocks:
+                k = start + int(rng.integers(0, count))
+                g = int(bad[k]) >> shift
+                g ^= g >> 1                                  # to Gray, flip one bit there, back to binary
+                g ^= 1 << int(rng.integers(0, P))
+                b = g
+                for s in (1, 2, 4, 8):
+                    b ^= b >> s
+                bad[k] = (b << shift) & 0xFFFF
+            n2, out2 = host_decode(L, (sf, ppm, rdd, 1, 0, 8, crc, 0), bad)
+            assert n2 == len(want) and out2 == want, ("corrected", sf, ppm, rdd, crc, ln)
