@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (0 = min(K, 100))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--simple", action="store_true", help="force the simple (non-fused) kernel")
+    ap.add_argument("--l2-resident", action="store_true",
+                    help="reuse ONE input buffer every step (fits the 126 MB L2 at the default size): the kernel's "
+                         "speed with DRAM out of the picture; not the headline (the default rotates > 3x L2)")
     ap.add_argument("--channels", type=int, default=1,
                     help="BASELINE config 4 form: this many independent channel buffers of --windows windows each, "
                          "demodulated by ONE lorab200_demod_multi_dev launch per step")
@@ -264,6 +267,8 @@ def main():
     step_bytes = nw * n * 8
     nbuf = max(2, int(np.ceil(3 * L2_BYTES / step_bytes)) + 1)
     nbuf = min(nbuf, 64)
+    if args.l2_resident:
+        nbuf = 1
     bufs, syms = [], []
     for b in range(nbuf):
         iq, s = synth_on_device(sf, nw, seed=0x10AA + 7919 * b + 104729 * rank, device=device)
@@ -405,8 +410,9 @@ def main():
         "config": {"workload": workload_name(sf, nw) if nch == 1 else
                    f"{nch} channels x SF={sf} x {wpc} windows per channel per GPU, one multi-channel launch per step",
                    "sf": sf, "windows_per_step_per_gpu": nw, "channels_per_gpu": nch,
-                   "l2": f"inputs rotate over {nbuf} distinct {step_bytes >> 20} MiB buffers "
-                         f"({nbuf * step_bytes >> 20} MiB > 3x L2), so every step streams from HBM",
+                   "l2": (f"inputs rotate over {nbuf} distinct {step_bytes >> 20} MiB buffers "
+                          f"({nbuf * step_bytes >> 20} MiB > 3x L2), so every step streams from HBM") if not args.l2_resident
+                   else f"ONE {step_bytes >> 20} MiB buffer reused every step (L2-resident, --l2-resident)",
                    "timing": "K steps captured in one CUDA graph (programmatic dependent launch between steps, LORAB200_FLAG_INPUT_STABLE), CUDA events on the launching stream",
                    "fine_step": args.fine_step,
                    "parity_spot_check": parity, "sharding": "windows block-partitioned per rank, no data-path collective"},
