@@ -226,7 +226,10 @@ void lorab200_pack_symbols(const lorab200_result *results, size_t n, int16_t *sy
  *         LORAB200_MOD_IDEAL      closed-form chirps (ovs must be 1), every sample
  *                                 independent, HBM write speed; differs from the reference
  *                                 waveform by the reference's own accumulated rounding.
- * Asynchronous on cuda_stream (NULL = CUDA's default stream).
+ *                                 iq_dev must be 16-byte aligned in this mode (two samples
+ *                                 per store), else LORAB200_ERR_INVALID.
+ * Asynchronous on cuda_stream (NULL = CUDA's default stream); no allocation or synchronous
+ * copy in IDEAL mode (legal inside a CUDA-graph capture).
  */
 #define LORAB200_MOD_REFERENCE 0
 #define LORAB200_MOD_IDEAL 1

@@ -173,10 +173,16 @@ LB_HD void codec_deinterleave(const uint16_t *sym, unsigned n_sym, uint8_t *cw, 
         }
 }
 
+// Byte scratch of decode_packet for n_cw codewords: one byte more than the n_cw / 2 the payload
+// can occupy.  With an explicit header, an even PPM and a packet of exactly one block the (8,4)
+// nibbles of the first block end on byte n_cw / 2 (LoRaDecoder.cpp:315-340 writes one byte past its
+// vector there); that byte is never part of the output, but it must not be another packet's.
+LB_HD unsigned codec_scratch_bytes(unsigned n_cw) { return n_cw / 2 + 1; }
+
 // LoRaDecoder.cpp:196-397.  `sym_io` holds n_in received symbols followed by room up to
 // codec_num_symbols() entries (it is modified in place), `cw` codec_num_codewords() bytes and
-// `bytes` (codec_num_codewords() + 1) / 2 bytes of scratch.  Returns the payload length written
-// to `out`, or one of the kDecode* codes.
+// `bytes` codec_scratch_bytes(codec_num_codewords()) bytes of scratch.  Returns the payload length
+// written to `out`, or one of the kDecode* codes.
 LB_HD int decode_packet(const DecoderCfg &c, uint16_t *sym_io, unsigned n_in, uint8_t *cw, uint8_t *bytes,
                         uint8_t *out, unsigned out_cap)
 {

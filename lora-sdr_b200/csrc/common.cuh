@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/lorab200.h"
 
 namespace lorab200 {
@@ -59,6 +61,26 @@ constexpr int kMaxSegments = LORAB200_MAX_SEGMENTS;
 template <bool MULTI> struct SegList { };
 template <> struct SegList<true> { const float2 *p[kMaxSegments]; };
 
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: every
+// launcher keeps one flag per device (contexts on different devices, and on different host
+// threads, are independent -- include/lorab200.h) and sets the attribute on first use there.
+constexpr int kMaxDevices = 64;
+struct SmemAttrOnce {
+    std::atomic<bool> done[kMaxDevices];
+    template <class Kernel>
+    cudaError_t ensure(Kernel kernel, int bytes)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const bool tracked = dev >= 0 && dev < kMaxDevices;
+        if (tracked && done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess && tracked) done[dev].store(true, std::memory_order_release);
+        return e;
+    }
+};
 
 // ---- exact complex arithmetic --------------------------------------------------
 __device__ __forceinline__ float2 cx_mul(float2 a, float2 b)
@@ -140,8 +162,15 @@ __device__ __forceinline__ void finalize_device(const RawResult &r, float power_
     const float fundamental = __fsqrt_rn(r.max_mag2);
     lorab200_result o;
     o.index = r.index;
+#ifdef LORAB200_K4
+    // 20*log10(sqrt(x)) = 10*log10(x) = 10*log10(2) * log2(x): one MUFU.LG2 per value
+    // (absolute error ~2^-22 in log2, i.e. < 1e-6 dB; the device-resident path's contract is 1e-4 dB)
+    o.power_avg = __fsub_rn(__fmul_rn(3.0102999566f, __log2f(__double2float_rn(__dsub_rn(r.total, double(r.max_mag2))))), power_scale);
+    o.power = __fsub_rn(__fmul_rn(3.0102999566f, __log2f(r.max_mag2)), power_scale);
+#else
     o.power_avg = __fsub_rn(__fmul_rn(20.0f, log10f(noise)), power_scale);
     o.power = __fsub_rn(__fmul_rn(20.0f, log10f(fundamental)), power_scale);
+#endif
     const float left = cx_abs(r.left), right = cx_abs(r.right);
     const double demon = __dsub_rn(__dsub_rn(__dmul_rn(2.0, double(fundamental)), double(right)), double(left));
     if (demon == 0.0) o.f_index = 0.0f;

@@ -38,6 +38,10 @@
 #include "common.cuh"
 #include "packed.cuh"
 
+#ifndef LORAB200_ABL
+#define LORAB200_ABL 0   // timing ablations (tools/build_variant.sh); results are wrong when non-zero
+#endif
+
 namespace lorab200 {
 
 // ---- compile-time geometry ---------------------------------------------------------
@@ -400,6 +404,8 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             if (uint32_t(lane) < raw_cnt) {
                 const RawResult rr = rawbuf[lane];
                 if (p.raw) p.raw[raw_w0 + lane] = rr;
+                if (LORAB200_ABL & 8) { if (p.out) { lorab200_result o; o.index = rr.index; o.power = rr.max_mag2; o.power_avg = float(rr.total); o.f_index = rr.left.x + rr.right.y; p.out[raw_w0 + lane] = o; } } // ablation: no dB math
+                else
                 if (p.out) finalize_device(rr, p.power_scale, &p.out[raw_w0 + lane]);
             }
         }
@@ -619,6 +625,7 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             float m2[16];
 #pragma unroll
             for (int y = 0; y < 16; ++y) m2[y] = pcx_mag2(r[y]);
+
             float bv; int by;
             {
                 float v8[8]; int i8[8];
@@ -650,6 +657,8 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
                 s0 += double(m2[y]); s1 += double(m2[y + 1]); s2 += double(m2[y + 2]); s3 += double(m2[y + 3]);
             }
             double sum = (s0 + s1) + (s2 + s3);
+            if (LORAB200_ABL & 1) sum = double(m2[0] + m2[5]);   // ablation: no double sum
+            if (LORAB200_ABL & 2) { bv = fmaxf(m2[3], m2[7]); by = int(__float_as_uint(m2[1]) & 15u); } // ablation: no tournament
             int bi = tL + G * by;
             if constexpr (DBG) {
                 if (p.fft && live) {
@@ -670,6 +679,21 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             } else {
+#ifdef LORAB200_K3
+                // value first: the window maximum (bv >= +0, never NaN: fmaxf is exact), then the
+                // smallest index among the lanes that hold it (the sequential scan's first-max rule)
+                float mv = bv;
+#pragma unroll
+                for (int o = WIDTH / 2; o > 0; o >>= 1) {
+                    mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+                    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                }
+                int cand = (bv == mv) ? bi : 0x7fffffff;
+#pragma unroll
+                for (int o = WIDTH / 2; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+                bv = mv;
+                bi = cand;
+#else
 #pragma unroll
                 for (int o = WIDTH / 2; o > 0; o >>= 1) {
                     const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -677,6 +701,7 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
                     sum += __shfl_xor_sync(0xffffffffu, sum, o);
                     argmax_merge(bv, bi, ov, oi);
                 }
+#endif
             }
             if constexpr (G > 32) {
                 // cross-warp: warp leaders publish one 16-byte partial {sum, value bits, index};
@@ -710,6 +735,8 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             const int tr = int(jr & unsigned(G - 1)), yr = int(jr >> (SF - 4));
             // (only the warps that hold one of the two owner lanes run the select tree)
             c64 nbv = r[0];
+            if (LORAB200_ABL & 4) nbv = r[5];                    // ablation: no neighbour select
+            else
             if (G <= 32 || __any_sync(0xffffffffu, tL == tl || tL == tr)) nbv = pick16(r, tL == tl ? yl : yr);
             // the record of this window is assembled in shared memory by the three lanes that
             // own its pieces; it is read back at the next flush (after a group-wide sync)
@@ -770,16 +797,16 @@ cudaError_t launch_fused_v(const DemodParams &p, const Pass0Tw &tw0, float2 phas
                            const SegList<MULTI> &segs = SegList<MULTI>())
 {
     using C = FusedCfg<SF>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(demod_fused_kernel<SF, DBG, FINE, MULTI>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+#ifdef LORAB200_EXP_1CTA   // occupancy experiment: one CTA per SM (tools/build_variant.sh)
+    constexpr int kSmem = 120 * 1024, kCtasPerSm = 1;
+#else
+    constexpr int kSmem = C::SMEM_BYTES, kCtasPerSm = C::CTAS_PER_SM;
+#endif
+    static SmemAttrOnce smem_attr; // per (instantiation, device)
+    if (cudaError_t e = smem_attr.ensure(demod_fused_kernel<SF, DBG, FINE, MULTI>, kSmem); e != cudaSuccess) return e;
     const unsigned long long n_tiles = (p.n_windows + C::WPT - 1) / C::WPT;
     unsigned long long ctas = (n_tiles + C::GROUPS - 1) / C::GROUPS;
-    const unsigned long long cap = (unsigned long long)C::CTAS_PER_SM * (unsigned long long)sm_count; // persistent
+    const unsigned long long cap = (unsigned long long)kCtasPerSm * (unsigned long long)sm_count; // persistent
     if (ctas > cap) ctas = cap;
     // Programmatic dependent launch: consecutive demod launches on a stream may overlap
     // this kernel's prologue (barrier init, table loads) with the previous kernel's tail;
@@ -787,7 +814,7 @@ cudaError_t launch_fused_v(const DemodParams &p, const Pass0Tw &tw0, float2 phas
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(ctas));
     cfg.blockDim = dim3(C::CTA);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.dynamicSmemBytes = kSmem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -4,6 +4,7 @@
 // replace LoRaDemod.cpp:157-172 with one call.  No torch types, no exceptions
 // across the ABI, no CPU fallback: if CUDA is unavailable create() fails.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <cstdio>
 #include <cmath>
@@ -53,7 +54,13 @@ public:
     ~Helpers() { stop(); }
     void ensure(size_t n)
     {
-        while (th_.size() < n) th_.emplace_back([this] { loop(); });
+        // a thread added later starts from the CURRENT generation: it must not take the pass that
+        // was published before it existed (fn_ would be null / the counters stale)
+        while (th_.size() < n) {
+            unsigned long g;
+            { std::lock_guard<std::mutex> l(m_); g = gen_; }
+            th_.emplace_back([this, g] { loop(g); });
+        }
     }
     // run fn(i) for i in [0, n) on the helpers plus the calling thread
     void parallel(size_t n, const std::function<void(size_t)> &fn)
@@ -80,9 +87,8 @@ public:
         th_.clear();
     }
 private:
-    void loop()
+    void loop(unsigned long seen)
     {
-        unsigned long seen = 0;
         for (;;) {
             const std::function<void(size_t)> *fn;
             size_t total;
@@ -113,7 +119,8 @@ private:
 } // namespace
 
 constexpr unsigned long long kFineSmallEntries = 8192; // fine prefix: closed form per entry up to here
-constexpr size_t kRingSlots = 4, kRingSlotBytes = size_t(512) << 10; // pageable-input staging ring
+constexpr size_t kRingSlots = 16, kRingSlotBytes = size_t(1) << 20; // pageable-input staging ring (16 MiB pinned)
+constexpr size_t kRingFillThreads = 6;                                // slots filled concurrently (helper threads)
 constexpr size_t kSmallBatchWindows = 16;          // lorab200_demod_host: zero-copy path up to here
 constexpr size_t kSmallBatchBytes = size_t(256) << 10;
 
@@ -147,7 +154,7 @@ struct lorab200_ctx {
     // pageable callers (a framework's ordinary port buffers): large H2D copies are staged through
     // a ring of pinned slots so that the PCIe copy of one slot overlaps the memcpy into the next
     void *h_ring = nullptr;
-    cudaEvent_t ring_free[4] = {};
+    cudaEvent_t ring_free[kRingSlots] = {};
     unsigned ring_next = 0;
     // walking fine-tune index (fine_prefix.cuh): T = g^16 for the cached step, two ping-pong
     // composition tables and the per-chunk states of the current batch
@@ -198,6 +205,19 @@ int ensure_pinned(lorab200_ctx *c, void *&p, size_t &cap, size_t bytes)
     return LORAB200_OK;
 }
 
+// CPUs this process may run on: respects the affinity mask a launcher gives each rank
+// (bench.py binds every rank to its GPU's NUMA node), unlike hardware_concurrency()
+size_t host_threads()
+{
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+        const int n = CPU_COUNT(&set);
+        if (n > 0) return size_t(n);
+    }
+    const unsigned h = std::thread::hardware_concurrency();
+    return h ? h : 1;
+}
+
 bool is_pageable(const void *p)
 {
     cudaPointerAttributes a;
@@ -218,14 +238,37 @@ int h2d_copy(lorab200_ctx *c, void *dst, const void *src, size_t bytes, cudaStre
         cudaError_t e = cudaMallocHost(&c->h_ring, kRingSlots * kRingSlotBytes);
         if (e != cudaSuccess) { (void)cudaGetLastError(); c->h_ring = nullptr; return fail(c, LORAB200_ERR_NOMEM, "cudaMallocHost(ring)", e); }
     }
-    for (size_t off = 0; off < bytes; off += kRingSlotBytes) {
-        const size_t len = bytes - off < kRingSlotBytes ? bytes - off : kRingSlotBytes;
-        const unsigned slot = c->ring_next++ % kRingSlots;
-        CU_TRY(c, cudaEventSynchronize(c->ring_free[slot])); // the copy that last used this slot is done
-        char *sp = static_cast<char *>(c->h_ring) + size_t(slot) * kRingSlotBytes;
-        std::memcpy(sp, static_cast<const char *>(src) + off, len);
-        CU_TRY(c, cudaMemcpyAsync(static_cast<char *>(dst) + off, sp, len, cudaMemcpyHostToDevice, s));
-        CU_TRY(c, cudaEventRecord(c->ring_free[slot], s));
+    // Groups of up to `par` slots: the helper threads (and this one) memcpy one slot each, then the
+    // slots' async copies are queued; the next group is filled while those copies run.  One thread
+    // moves ~12 GB/s (measured, round 1), PCIe gen5 takes ~50: a handful of threads keep it busy.
+    size_t par = host_threads() / 2;
+    if (par > kRingFillThreads) par = kRingFillThreads;
+    if (par < 1) par = 1;
+    if (par > 1) c->helpers.ensure(par - 1);
+    for (size_t off = 0; off < bytes;) {
+        size_t n_slots = (bytes - off + kRingSlotBytes - 1) / kRingSlotBytes;
+        if (n_slots > par) n_slots = par;
+        unsigned slot[kRingFillThreads];
+        for (size_t i = 0; i < n_slots; ++i) {
+            slot[i] = c->ring_next++ % kRingSlots;
+            CU_TRY(c, cudaEventSynchronize(c->ring_free[slot[i]])); // the copy that last used this slot is done
+        }
+        const char *from = static_cast<const char *>(src) + off;
+        const size_t left = bytes - off;
+        char *ring = static_cast<char *>(c->h_ring);
+        const std::function<void(size_t)> fill = [&](size_t i) {
+            const size_t o = i * kRingSlotBytes, len = left - o < kRingSlotBytes ? left - o : kRingSlotBytes;
+            std::memcpy(ring + size_t(slot[i]) * kRingSlotBytes, from + o, len);
+        };
+        if (n_slots > 1) c->helpers.parallel(n_slots, fill);
+        else fill(0);
+        for (size_t i = 0; i < n_slots; ++i) {
+            const size_t o = i * kRingSlotBytes, len = left - o < kRingSlotBytes ? left - o : kRingSlotBytes;
+            CU_TRY(c, cudaMemcpyAsync(static_cast<char *>(dst) + off + o, ring + size_t(slot[i]) * kRingSlotBytes, len,
+                                      cudaMemcpyHostToDevice, s));
+            CU_TRY(c, cudaEventRecord(c->ring_free[slot[i]], s));
+        }
+        off += n_slots * kRingSlotBytes;
     }
     return LORAB200_OK;
 }
@@ -248,13 +291,8 @@ cudaError_t launch_simple_sf(const DemodParams &p, cudaStream_t s, int sm_count,
 {
     constexpr int N = 1 << SF;
     const size_t smem = size_t(N) * sizeof(float2) + size_t(N) * sizeof(int);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(demod_simple_kernel<SF, MULTI>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    static SmemAttrOnce attr;
+    if (cudaError_t e = attr.ensure(demod_simple_kernel<SF, MULTI>, int(smem)); e != cudaSuccess) return e;
     unsigned long long grid = p.n_windows;
     const unsigned long long cap = (unsigned long long)sm_count * 64ull;
     if (grid > cap) grid = cap; // grid-stride over windows
@@ -283,12 +321,8 @@ cudaError_t launch_rx_sf(const RxParams &p, cudaStream_t s, int sm_count)
 {
     constexpr int N = 1 << SF;
     const size_t smem = size_t(N) * sizeof(float2) + size_t(N) * sizeof(int);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(rx_kernel<SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    static SmemAttrOnce attr;
+    if (cudaError_t e = attr.ensure(rx_kernel<SF>, int(smem)); e != cudaSuccess) return e;
     unsigned grid = p.n_channels;
     const unsigned cap = unsigned(sm_count) * 16u;
     if (grid > cap) grid = cap;
@@ -525,6 +559,21 @@ int lorab200_create(lorab200_ctx **out, int device, int sf, uint32_t flags)
         build_twiddles(sf, c->h_table[LORAB200_TABLE_TWIDDLE]);
         for (int t = 0; t < 4 && st == LORAB200_OK; ++t) {
             st = upload_table(c, t);
+            if (st) g_create_error = c->err;
+        }
+        if (st == LORAB200_OK) {
+            // modulator, IDEAL mode: exp(j*pi*m/N), m < 2N -- the 2N-point constellation every ideal chirp
+            // sample lies on.  Built here (not on first use) so that lorab200_mod_dev never allocates or
+            // copies synchronously: it stays legal inside a CUDA-graph capture.
+            std::vector<float2> e(2 * c->n);
+            for (size_t m = 0; m < e.size(); ++m) {
+                const double a = M_PI * double(m) / double(c->n);
+                e[m] = make_float2(float(std::cos(a)), float(std::sin(a)));
+            }
+            st = ensure_dev(c, c->d_mod_phasor, e.size() * sizeof(float2));
+            if (st == LORAB200_OK &&
+                cudaMemcpy(c->d_mod_phasor.p, e.data(), e.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess)
+                st = fail(c, LORAB200_ERR_CUDA, "upload of the modulator phasor table");
             if (st) g_create_error = c->err;
         }
     } while (0);
@@ -777,7 +826,7 @@ int lorab200_decode_dev(lorab200_ctx *c, const uint16_t *symbols_dev, size_t n_p
     p.lengths = lengths_dev;
     p.max_sym = codec_num_symbols(p.cfg, p.sym_stride);
     p.max_cw = codec_num_codewords(p.cfg, p.sym_stride);
-    p.max_bytes = (p.max_cw + 1) / 2;
+    p.max_bytes = codec_scratch_bytes(p.max_cw);
     const size_t sym_bytes = (size_t(p.max_sym) * 2 * n_packets + 15) & ~size_t(15);
     const size_t cw_bytes = (size_t(p.max_cw) * n_packets + 15) & ~size_t(15);
     int st;
@@ -887,16 +936,10 @@ int lorab200_mod_dev(lorab200_ctx *c, const uint16_t *symbols_dev, size_t n_pack
         return unsigned(b < 1 ? 1 : (b > cap ? cap : b));
     };
     if (mode == LORAB200_MOD_IDEAL) {
-        if (!c->d_mod_phasor.p) {
-            // exp(j*pi*m/N), m < 2N: the 2N-point constellation every ideal chirp sample lies on
-            std::vector<float2> e(2 * c->n);
-            for (size_t m = 0; m < e.size(); ++m) {
-                const double a = M_PI * double(m) / double(c->n);
-                e[m] = make_float2(float(std::cos(a)), float(std::sin(a)));
-            }
-            if ((st = ensure_dev(c, c->d_mod_phasor, e.size() * sizeof(float2)))) return st;
-            CU_TRY(c, cudaMemcpy(c->d_mod_phasor.p, e.data(), e.size() * sizeof(float2), cudaMemcpyHostToDevice));
-        }
+        // two samples per 128-bit store (mod_synth.cuh): packets start on 16-byte boundaries
+        // (samples_per_packet is a multiple of 32), so only the base needs checking
+        if ((reinterpret_cast<uintptr_t>(iq_dev) & 15u) != 0)
+            return fail(c, LORAB200_ERR_INVALID, "LORAB200_MOD_IDEAL needs a 16-byte aligned iq_dev");
         p.phasor = static_cast<const float2 *>(c->d_mod_phasor.p);
         const unsigned bpp = unsigned((p.samples_per_packet + kModIdealSpan - 1) / kModIdealSpan);
         const unsigned long long nb = p.n_packets * bpp;
@@ -1024,7 +1067,7 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     };
     const size_t n_tasks = n_chunks * per_chunk;
     if (n_windows >= 16384 && n_chunks >= 4) {
-        size_t n_thr = std::thread::hardware_concurrency() / 4;
+        size_t n_thr = host_threads() / 4;
         if (n_thr > 8) n_thr = 8;
         if (n_thr > n_tasks) n_thr = n_tasks;
         if (n_thr < 2) n_thr = 2;

@@ -17,8 +17,13 @@ extern "C" int codec_host_decode(const int32_t *cfg8 /* sf, ppm, rdd, explicit, 
     const unsigned n = unsigned(n_symbols < 0 ? 0 : n_symbols);
     std::vector<uint16_t> sym(lorab200::codec_num_symbols(c, n) + 16);
     std::memcpy(sym.data(), symbols, size_t(n) * 2);
-    std::vector<uint8_t> cw(lorab200::codec_num_codewords(c, n) + 16), bytes(cw.size() / 2 + 16);
-    return lorab200::decode_packet(c, sym.data(), n, cw.data(), bytes.data(), out, unsigned(out_cap));
+    // exact sizes plus one guard byte each: an overrun of either scratch is reported as -100
+    const unsigned n_cw = lorab200::codec_num_codewords(c, n), n_b = lorab200::codec_scratch_bytes(n_cw);
+    std::vector<uint8_t> cw(n_cw + 1), bytes(n_b + 1);
+    cw[n_cw] = 0xA5; bytes[n_b] = 0x5A;
+    const int r = lorab200::decode_packet(c, sym.data(), n, cw.data(), bytes.data(), out, unsigned(out_cap));
+    if (cw[n_cw] != 0xA5 || bytes[n_b] != 0x5A) return -100;
+    return r;
 }
 
 extern "C" int codec_host_encode(const int32_t *cfg6 /* sf, ppm, rdd, explicit, crc, whitening */,

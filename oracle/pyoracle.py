@@ -23,6 +23,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 LIB_ORACLE = HERE / "liblora_oracle.so"
 LIB_REF = HERE / "_ref" / "libloraref.so"
+LIB_REF_O3 = HERE / "_ref" / "libloraref_o3.so"   # -O3 -march=x86-64-v3 courtesy build (same results)
 
 RESULT_DTYPE = np.dtype(
     [("index", "<i4"), ("power", "<f4"), ("power_avg", "<f4"), ("f_index", "<f4")]
@@ -173,11 +174,12 @@ class Reference(Oracle):
 
     kind = "reference"
 
-    def __init__(self):
+    def __init__(self, o3: bool = False):
         super().__init__()
-        if not LIB_REF.exists():
-            raise FileNotFoundError(f"{LIB_REF} not built (needs /root/reference)")
-        self.ref = C.CDLL(str(LIB_REF))
+        lib = LIB_REF_O3 if o3 else LIB_REF
+        if not lib.exists():
+            raise FileNotFoundError(f"{lib} not built (needs /root/reference)")
+        self.ref = C.CDLL(str(lib))
         R = self.ref
         R.ref_fft.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         R.ref_detect.restype = C.c_size_t

@@ -193,3 +193,23 @@ def test_codec_round_trip_and_single_error_correction():
                 bad[k] = (b << shift) & 0xFFFF
             n2, out2 = host_decode(L, (sf, ppm, rdd, 1, 0, 8, crc, 0), bad)
             assert n2 == len(want) and out2 == want, ("corrected", sf, ppm, rdd, crc, ln)
+
+
+@needs_chain
+@pytest.mark.parametrize("sf", [8, 10, 12])
+def test_one_block_explicit_packets_stay_inside_the_scratch(sf):
+    """Explicit header, rdd = 4, even PPM, exactly 8 symbols: the first block's (8,4) nibbles end on
+    byte n_cw / 2 (the reference writes one byte past its vector there, LoRaDecoder.cpp:315-340).
+    codec_host_decode sizes both scratch areas exactly with a guard byte behind each and returns
+    -100 if a guard was touched."""
+    L = host_codec()
+    rng = np.random.default_rng(sf)
+    for ppm in (0, sf - 2):
+        for hdr, crcc, echk in itertools.product((0, 1), (0, 1), (0, 1)):
+            cfg = (sf, ppm, 4, 1, hdr, 11, crcc, echk)
+            for _ in range(6):
+                syms = rng.integers(0, 1 << sf, 8).astype(np.uint16)
+                n, data = host_decode(L, cfg, syms)
+                assert n != -100, ("scratch overrun", cfg)
+                exp_len, exp = loopback.decode(cfg, syms)
+                assert n == exp_len and (n <= 0 or data == exp), (cfg, n, exp_len)

@@ -158,3 +158,30 @@ def test_transmit_and_receive_chains_on_the_device(lib, cuda_ok):
         ref = loopback.receive(sf, 4, host_iq[c], use_b200=False, debug_ports=True, mtu=128)
         assert ref["decoded"] and ref["decoded"][0][:ln] == bytes(payloads[c])
     d.close()
+
+
+@needs_chain
+@pytest.mark.parametrize("sf", [8, 10, 12])
+def test_decode_dev_one_block_packets_packed_at_stride_8(lib, cuda_ok, sf):
+    """A batch of 8-symbol explicit packets at symbols_stride == 8 (even PPM, rdd 4): packet p's first
+    block ends on the byte behind its payload scratch; it must not land in packet p+1's header byte
+    (per-packet scratch = codec_scratch_bytes).  Every packet must decode as it does alone."""
+    import torch
+    rng = np.random.default_rng(sf + 77)
+    n_pk = 64
+    clean = loopback.encode(sf, 4, bytes([1, 2, 3]))[:8]        # a valid header block of a short packet
+    host = rng.integers(0, 1 << sf, (n_pk, 8)).astype(np.uint16)
+    host[::3] = clean
+    lens = np.full(n_pk, 8, np.int32)
+    cfg = (sf, 0, 4, 1, 1, 9, 0, 0)
+    d = lib.Demod(sf)
+    out, got_len = d.decode_dev(torch.from_numpy(host.view(np.int16)).cuda(), torch.from_numpy(lens).cuda(),
+                                ppm=0, rdd=4, explicit_header=True, hdr=True, data_length=9, crcc=False,
+                                error_check=False, bytes_stride=64)
+    out, got_len = out.cpu().numpy(), got_len.cpu().numpy()
+    for i in range(n_pk):
+        exp_len, exp = loopback.decode(cfg, host[i])
+        assert got_len[i] == exp_len, (i, got_len[i], exp_len)
+        if exp_len > 0:
+            assert bytes(out[i, :exp_len]) == exp, i
+    d.close()

@@ -79,3 +79,22 @@ def test_demod_tables_match_real_block(oracle, reference, sf):
     ou, od = oracle.tables_demod(sf)
     assert bits_equal(up, ou) and bits_equal(down, od)
     assert bits_equal(fine, oracle.table_fine(sf))
+
+
+@pytest.mark.parametrize("sf", [7, 10, 12])
+def test_o3_avx2_courtesy_build_gives_the_same_bits(reference, sf):
+    """The -O3 -march=x86-64-v3 build of the reference shim (bench.py's cpu_baseline.o3_avx2 figure)
+    must not change a single result bit: no fast-math, no FMA contraction."""
+    from oracle import pyoracle
+    from util import synth_windows
+    try:
+        o3 = pyoracle.Reference(o3=True)
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/libloraref_o3.so not built")
+    nw = 64 if sf <= 10 else 12
+    iq, _ = synth_windows(sf, nw, seed=sf + 1, snr_db=-3.0)
+    up, _ = reference.tables_demod(sf)
+    a, _, fa, _ = reference.demod_windows(sf, iq, nw, up, want_fft=True)
+    b, _, fb, _ = o3.demod_windows(sf, iq, nw, up, want_fft=True)
+    assert a.tobytes() == b.tobytes()
+    assert fa.tobytes() == fb.tobytes()
