@@ -150,27 +150,21 @@ __device__ __forceinline__ float cx_abs(float2 a)
     return __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y))));
 }
 
-// LoRaDetector.hpp:50-61 on the device.  index and f_index are bit-exact; power and
-// power_avg use the device log10f (<= 2 ulp) where the reference uses glibc's log10f
-// (not correctly rounded either), so they may differ from the reference by a few
-// 1e-6 dB (tests allow 1e-4 dB).  lorab200_demod_host finalises on the host instead
-// and is bit-exact.
+// LoRaDetector.hpp:50-61 on the device.  index and f_index are bit-exact.  power and
+// power_avg: 20*log10(sqrt(x)) - scale is evaluated as 10*log10(2)*log2(x) - scale with one
+// MUFU.LG2 per value (absolute error ~2^-22 in log2, i.e. about 1e-6 dB) where the reference
+// calls glibc's sqrtf and log10f (not correctly rounded either): the device-resident path's
+// contract is 1e-4 dB (tests/test_gpu_parity.py POWER_TOL_DB).  lorab200_demod_host finalises
+// on the host with the host libm instead and is bit-exact.
 __device__ __forceinline__ void finalize_device(const RawResult &r, float power_scale,
                                                 lorab200_result *out)
 {
-    const float noise = __fsqrt_rn(__double2float_rn(__dsub_rn(r.total, double(r.max_mag2))));
     const float fundamental = __fsqrt_rn(r.max_mag2);
     lorab200_result o;
     o.index = r.index;
-#ifdef LORAB200_K4
-    // 20*log10(sqrt(x)) = 10*log10(x) = 10*log10(2) * log2(x): one MUFU.LG2 per value
-    // (absolute error ~2^-22 in log2, i.e. < 1e-6 dB; the device-resident path's contract is 1e-4 dB)
-    o.power_avg = __fsub_rn(__fmul_rn(3.0102999566f, __log2f(__double2float_rn(__dsub_rn(r.total, double(r.max_mag2))))), power_scale);
-    o.power = __fsub_rn(__fmul_rn(3.0102999566f, __log2f(r.max_mag2)), power_scale);
-#else
-    o.power_avg = __fsub_rn(__fmul_rn(20.0f, log10f(noise)), power_scale);
-    o.power = __fsub_rn(__fmul_rn(20.0f, log10f(fundamental)), power_scale);
-#endif
+    const float kDbPerLog2 = 3.0102999566f; // 10*log10(2)
+    o.power_avg = __fsub_rn(__fmul_rn(kDbPerLog2, __log2f(__double2float_rn(__dsub_rn(r.total, double(r.max_mag2))))), power_scale);
+    o.power = __fsub_rn(__fmul_rn(kDbPerLog2, __log2f(r.max_mag2)), power_scale);
     const float left = cx_abs(r.left), right = cx_abs(r.right);
     const double demon = __dsub_rn(__dsub_rn(__dmul_rn(2.0, double(fundamental)), double(right)), double(left));
     if (demon == 0.0) o.f_index = 0.0f;

@@ -7,11 +7,13 @@
 #include <sched.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <limits>
 #include <cstring>
 #include <new>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -57,8 +59,7 @@ public:
         // a thread added later starts from the CURRENT generation: it must not take the pass that
         // was published before it existed (fn_ would be null / the counters stale)
         while (th_.size() < n) {
-            unsigned long g;
-            { std::lock_guard<std::mutex> l(m_); g = gen_; }
+            const unsigned long g = gen_.load(std::memory_order_acquire);
             th_.emplace_back([this, g] { loop(g); });
         }
     }
@@ -67,7 +68,8 @@ public:
     {
         {
             std::lock_guard<std::mutex> l(m_);
-            fn_ = &fn; next_ = 0; total_ = n; busy_ = th_.size(); ++gen_;
+            fn_ = &fn; next_ = 0; total_ = n; busy_ = th_.size();
+            gen_.fetch_add(1, std::memory_order_release);
         }
         cv_.notify_all();
         for (;;) {
@@ -81,7 +83,7 @@ public:
     }
     void stop()
     {
-        { std::lock_guard<std::mutex> l(m_); quit_ = true; ++gen_; }
+        { std::lock_guard<std::mutex> l(m_); quit_ = true; gen_.fetch_add(1, std::memory_order_release); }
         cv_.notify_all();
         for (auto &t : th_) t.join();
         th_.clear();
@@ -90,12 +92,23 @@ private:
     void loop(unsigned long seen)
     {
         for (;;) {
+            // Passes come in bursts (one per 6 MiB of a pageable batch, ~150 us apart): a helper that
+            // has just finished one spins for a short while before it goes back to sleep on the
+            // condition variable, whose wake-up (~100 us) is as long as the task it would be given.
+            const auto spin_until = std::chrono::steady_clock::now() + std::chrono::microseconds(400);
+            bool fresh = false;
+            for (unsigned i = 0;; ++i) {
+                if (gen_.load(std::memory_order_acquire) != seen) { fresh = true; break; }
+                if ((i & 63u) == 63u && std::chrono::steady_clock::now() > spin_until) break;
+                // (no PAUSE instruction here: under a hypervisor with pause-loop exiting it made a pass
+                //  3x SLOWER than not spinning at all; a plain polling loop costs one core for <= 400 us)
+            }
             const std::function<void(size_t)> *fn;
             size_t total;
             {
                 std::unique_lock<std::mutex> l(m_);
-                cv_.wait(l, [&] { return gen_ != seen; });
-                seen = gen_;
+                if (!fresh) cv_.wait(l, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+                seen = gen_.load(std::memory_order_acquire);
                 if (quit_) return;
                 fn = fn_; total = total_;
             }
@@ -113,14 +126,14 @@ private:
     const std::function<void(size_t)> *fn_ = nullptr;
     std::atomic<size_t> next_{0};
     size_t total_ = 0, busy_ = 0;
-    unsigned long gen_ = 0;
+    std::atomic<unsigned long> gen_{0};
     bool quit_ = false;
 };
 } // namespace
 
 constexpr unsigned long long kFineSmallEntries = 8192; // fine prefix: closed form per entry up to here
 constexpr size_t kRingSlots = 16, kRingSlotBytes = size_t(1) << 20; // pageable-input staging ring (16 MiB pinned)
-constexpr size_t kRingFillThreads = 6;                                // slots filled concurrently (helper threads)
+constexpr size_t kRingFillThreads = 8;                                // slots filled concurrently (helper threads)
 constexpr size_t kSmallBatchWindows = 16;          // lorab200_demod_host: zero-copy path up to here
 constexpr size_t kSmallBatchBytes = size_t(256) << 10;
 
@@ -245,7 +258,11 @@ int h2d_copy(lorab200_ctx *c, void *dst, const void *src, size_t bytes, cudaStre
     if (par > kRingFillThreads) par = kRingFillThreads;
     if (par < 1) par = 1;
     if (par > 1) c->helpers.ensure(par - 1);
+    static const bool trace = std::getenv("LORAB200_TRACE") != nullptr;
+    using clk = std::chrono::steady_clock;
+    double t_wait = 0, t_fill = 0, t_enq = 0;
     for (size_t off = 0; off < bytes;) {
+        const auto ta = clk::now();
         size_t n_slots = (bytes - off + kRingSlotBytes - 1) / kRingSlotBytes;
         if (n_slots > par) n_slots = par;
         unsigned slot[kRingFillThreads];
@@ -253,6 +270,7 @@ int h2d_copy(lorab200_ctx *c, void *dst, const void *src, size_t bytes, cudaStre
             slot[i] = c->ring_next++ % kRingSlots;
             CU_TRY(c, cudaEventSynchronize(c->ring_free[slot[i]])); // the copy that last used this slot is done
         }
+        const auto tb = clk::now();
         const char *from = static_cast<const char *>(src) + off;
         const size_t left = bytes - off;
         char *ring = static_cast<char *>(c->h_ring);
@@ -262,6 +280,7 @@ int h2d_copy(lorab200_ctx *c, void *dst, const void *src, size_t bytes, cudaStre
         };
         if (n_slots > 1) c->helpers.parallel(n_slots, fill);
         else fill(0);
+        const auto tc = clk::now();
         for (size_t i = 0; i < n_slots; ++i) {
             const size_t o = i * kRingSlotBytes, len = left - o < kRingSlotBytes ? left - o : kRingSlotBytes;
             CU_TRY(c, cudaMemcpyAsync(static_cast<char *>(dst) + off + o, ring + size_t(slot[i]) * kRingSlotBytes, len,
@@ -269,7 +288,16 @@ int h2d_copy(lorab200_ctx *c, void *dst, const void *src, size_t bytes, cudaStre
             CU_TRY(c, cudaEventRecord(c->ring_free[slot[i]], s));
         }
         off += n_slots * kRingSlotBytes;
+        if (trace) {
+            const auto td = clk::now();
+            t_wait += std::chrono::duration<double>(tb - ta).count();
+            t_fill += std::chrono::duration<double>(tc - tb).count();
+            t_enq += std::chrono::duration<double>(td - tc).count();
+        }
     }
+    if (trace)
+        std::fprintf(stderr, "lorab200 trace: staged %.1f MiB with %zu thread(s): slot wait %.0f us, fill %.0f us (%.1f GB/s), enqueue %.0f us\n",
+                     bytes / 1048576.0, par, t_wait * 1e6, t_fill * 1e6, bytes / (t_fill > 0 ? t_fill : 1) / 1e9, t_enq * 1e6);
     return LORAB200_OK;
 }
 

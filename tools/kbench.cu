@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <string>
@@ -83,6 +84,8 @@ int main(int argc, char **argv)
     unsigned flags = LORAB200_FLAG_INPUT_STABLE;
     float fine_step = 0.f; bool use_fine = false;
     const char *tag = "";
+    bool print_reps = false;
+    int idle_ms = 0;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto nxt = [&]() { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
@@ -94,6 +97,8 @@ int main(int argc, char **argv)
         else if (a == "--flags") flags = unsigned(atoi(nxt()));
         else if (a == "--fine-step") { fine_step = float(atof(nxt())); use_fine = true; }
         else if (a == "--tag") tag = nxt();
+        else if (a == "--print-reps") print_reps = true;
+        else if (a == "--idle-ms") idle_ms = atoi(nxt());
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
     Api api;
@@ -153,11 +158,17 @@ int main(int argc, char **argv)
             CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
             std::vector<float> ms(reps);
             for (int r = 0; r < reps; ++r) {
+                if (idle_ms) { struct timespec ts = {idle_ms / 1000, (idle_ms % 1000) * 1000000L}; nanosleep(&ts, nullptr); }
                 CK(cudaEventRecord(e0, st));
                 CK(cudaGraphLaunch(ge, st));
                 CK(cudaEventRecord(e1, st));
                 CK(cudaStreamSynchronize(st));
                 CK(cudaEventElapsedTime(&ms[r], e0, e1));
+            }
+            if (print_reps) {
+                printf("reps_us:");
+                for (int r = 0; r < reps; ++r) printf(" %.2f", ms[r] * 1e3 / steps);
+                printf("\n");
             }
             std::sort(ms.begin(), ms.end());
             const double us = ms[reps / 2] * 1e3 / steps, us_best = ms[0] * 1e3 / steps;
