@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define LORAB200_ABI_VERSION 1
+#define LORAB200_ABI_VERSION 2 /* 2: lorab200_rx_state / lorab200_rx_packet carry the raw peak and total; lorab200_rx_host */
 
 typedef struct lorab200_ctx lorab200_ctx;
 
@@ -247,12 +247,16 @@ typedef struct lorab200_rx_state {
     float ffe;
     int32_t sig_error;
     float sig_power, sig_snr;
+    float sig_max_mag2, sig_reserved;  /* raw peak |bin|^2 and double sum of |bin|^2 of the window the */
+    double sig_total;                  /* signals were taken from (host-side, libm-exact dB values)     */
 } lorab200_rx_state;
 
 typedef struct lorab200_rx_packet {
-    int32_t length;       /* symbols in the packet (the Packet's payload.length / 2) */
+    int32_t length;       /* symbols in the packet (the Packet's payload.length / 2); 0 = unused slot */
     int32_t error;        /* the "error" signal emitted for this packet (LoRaDemod.cpp:267) */
     float power, snr;     /* the "power" and "snr" signals (:268-269) */
+    float max_mag2, reserved; /* raw detector outputs behind power / snr (LoRaDetector.hpp:42-54) */
+    double total;
 } lorab200_rx_packet;
 
 /*
@@ -267,14 +271,32 @@ typedef struct lorab200_rx_packet {
  *   symbols_dev  [n_channels][max_packets][mtu] int16: packet p of channel c, info_dev[c][p].length symbols
  *   setSync / setThreshold / setMTU are the sync, thresh_db, mtu arguments.
  * Symbols, packet boundaries and the error signal are bit-identical to the reference block's;
- * power/snr use the device log10f (within 1e-4 dB), so a squelch decision can differ only when
- * snr is within that distance of thresh_db.  Asynchronous on cuda_stream.
+ * power/snr use the device logarithm (within 1e-4 dB), so a squelch decision can differ only when
+ * snr is within that distance of thresh_db; max_mag2 / total are the raw values behind them.
+ * info_dev slots at and beyond n_packets_dev[c] are written with length 0; when max_packets packets
+ * were written, more than 2N samples may remain unconsumed.  Asynchronous on cuda_stream.
  */
 int lorab200_rx_dev(lorab200_ctx *ctx, const void *iq_dev, size_t n_channels, size_t channel_stride_samples,
                     size_t n_samples, unsigned sync, float thresh_db, size_t mtu,
                     lorab200_rx_state *state_dev, int16_t *partial_dev, int16_t *symbols_dev,
                     lorab200_rx_packet *info_dev, int32_t *n_packets_dev, uint64_t *consumed_dev,
                     size_t max_packets, void *cuda_stream);
+
+/*
+ * The same receiver for HOST buffers -- what a block's work() calls (LoRaDemod.cpp:145-327 for the whole
+ * input buffer in one call): channel c's samples are read from iq_list[c] (n_samples complex64 each,
+ * pageable or page-locked), staged to the device, received by ONE launch, and the results come back
+ * in the caller's host arrays (same shapes as lorab200_rx_dev's, all HOST memory; state and partial
+ * are in/out and carry a stream from call to call).  power / snr of every packet (and sig_power /
+ * sig_snr of the state) are recomputed from the raw values with the HOST libm: bit-identical to
+ * the reference block's signals.  Synchronous: returns when the packets are there.
+ * consumed[c] samples of channel c have been used; present the rest again, in front of the new
+ * samples, at the next call (a Pothos block: inPort->consume(consumed)).
+ */
+int lorab200_rx_host(lorab200_ctx *ctx, const float *const *iq_list, size_t n_channels, size_t n_samples,
+                     unsigned sync, float thresh_db, size_t mtu, lorab200_rx_state *state, int16_t *partial,
+                     int16_t *symbols, lorab200_rx_packet *info, int32_t *n_packets, uint64_t *consumed,
+                     size_t max_packets);
 
 /* ---- decoder ------------------------------------- */
 

@@ -52,7 +52,7 @@ EXPORTS = [
     "lorab200_gen_chirp", "lorab200_demod_dev", "lorab200_demod_host", "lorab200_pack_symbols",
     "lorab200_kernel_launches", "lorab200_last_kernel", "lorab200_alloc_pinned",
     "lorab200_free_pinned", "lorab200_table_len", "lorab200_build_table", "lorab200_fine_advance",
-    "lorab200_demod_multi_dev", "lorab200_mod_samples", "lorab200_mod_dev", "lorab200_decode_dev", "lorab200_rx_dev", "lorab200_encode_dev", "lorab200_encode_symbols",
+    "lorab200_demod_multi_dev", "lorab200_mod_samples", "lorab200_mod_dev", "lorab200_decode_dev", "lorab200_rx_dev", "lorab200_rx_host", "lorab200_encode_dev", "lorab200_encode_symbols",
 ]
 
 
@@ -144,6 +144,7 @@ def load_library() -> C.CDLL:
     L.lorab200_demod_multi_dev.argtypes = [vp, C.POINTER(vp), sz, sz, sz, C.c_int, vp, vp]
     L.lorab200_decode_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, vp, vp]
     L.lorab200_rx_dev.argtypes = [vp, vp, sz, sz, sz, C.c_uint, C.c_float, sz, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.lorab200_rx_host.argtypes = [vp, vp, sz, sz, C.c_uint, C.c_float, sz, vp, vp, vp, vp, vp, vp, sz]
     L.lorab200_encode_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, vp, vp]
     L.lorab200_encode_symbols.restype = sz
     L.lorab200_encode_symbols.argtypes = [C.c_int, vp, sz]
@@ -323,8 +324,8 @@ class Demod:
     # ---- receiver: frame sync + symbol extraction on the device (LoRaDemod.cpp:145-327) -----------------
     def rx_dev(self, iq, n_samples=None, sync=0x12, thresh=-30.0, mtu=256, max_packets=16, state=None, stream=None):
         """iq: CUDA complex64 tensor [n_channels, samples].  Returns a dict of CUDA tensors: symbols
-        [n_channels, max_packets, mtu] int16, info [n_channels, max_packets, 4] int32 words (length, error, power
-        bits, snr bits), n_packets [n_channels], consumed [n_channels], state (pass it back in to continue)."""
+        [n_channels, max_packets, mtu] int16, info [n_channels, max_packets, 8] int32 words (length, error, power
+        bits, snr bits, raw peak bits, 0, raw total as a double), n_packets [n_channels], consumed [n_channels], state (pass it back in to continue)."""
         import torch
 
         assert iq.is_cuda and iq.is_contiguous() and iq.dim() == 2
@@ -332,10 +333,10 @@ class Demod:
         n_samples = stride if n_samples is None else int(n_samples)
         dev = iq.device
         if state is None:
-            state = {"state": torch.zeros((nch, 10), dtype=torch.int32, device=dev),
+            state = {"state": torch.zeros((nch, 14), dtype=torch.int32, device=dev),
                      "partial": torch.zeros((nch, mtu), dtype=torch.int16, device=dev)}
         symbols = torch.zeros((nch, max_packets, mtu), dtype=torch.int16, device=dev)
-        info = torch.zeros((nch, max_packets, 4), dtype=torch.int32, device=dev)
+        info = torch.zeros((nch, max_packets, 8), dtype=torch.int32, device=dev)
         n_packets = torch.zeros(nch, dtype=torch.int32, device=dev)
         consumed = torch.zeros(nch, dtype=torch.int64, device=dev)
         if stream is None:
@@ -346,6 +347,28 @@ class Demod:
                                     C.c_void_p(n_packets.data_ptr()), C.c_void_p(consumed.data_ptr()), max_packets,
                                     C.c_void_p(stream))
         self._check(st, "rx_dev")
+        return dict(symbols=symbols, info=info, n_packets=n_packets, consumed=consumed, state=state)
+
+    def rx_host(self, iq_list, sync=0x12, thresh=-30.0, mtu=256, max_packets=16, state=None):
+        """Host-buffer twin of :meth:`rx_dev`: iq_list = one contiguous complex64 numpy array per channel, all of
+        the same length.  Returns a dict of numpy arrays (symbols, info, n_packets, consumed, state)."""
+        nch = len(iq_list)
+        arrs = [np.ascontiguousarray(a, dtype=np.complex64) for a in iq_list]
+        n_samples = arrs[0].size
+        assert all(a.size == n_samples for a in arrs)
+        if state is None:
+            state = {"state": np.zeros((nch, 14), np.int32), "partial": np.zeros((nch, mtu), np.int16)}
+        ptrs = (C.c_void_p * nch)(*[a.ctypes.data for a in arrs])
+        symbols = np.zeros((nch, max_packets, mtu), np.int16)
+        info = np.zeros((nch, max_packets, 8), np.int32)
+        n_packets = np.zeros(nch, np.int32)
+        consumed = np.zeros(nch, np.uint64)
+        vp = C.c_void_p
+        st = self.L.lorab200_rx_host(self.ctx, ptrs, nch, n_samples, sync, thresh, mtu,
+                                     vp(state["state"].ctypes.data), vp(state["partial"].ctypes.data),
+                                     vp(symbols.ctypes.data), vp(info.ctypes.data), vp(n_packets.ctypes.data),
+                                     vp(consumed.ctypes.data), max_packets)
+        self._check(st, "rx_host")
         return dict(symbols=symbols, info=info, n_packets=n_packets, consumed=consumed, state=state)
 
     # ---- encoder (LoRaEncoder.cpp) ----------------------------------------------------------------

@@ -36,6 +36,7 @@
 //     window running the double-precision log10 alone.
 #pragma once
 #include "common.cuh"
+#include "fine_orbit.h"
 #include "packed.cuh"
 
 #ifndef LORAB200_ABL
@@ -252,7 +253,16 @@ __device__ __forceinline__ c64 pick16(const c64 (&r)[16], int slot)
 //              thread t of a window walks chunk t with the literal recurrence and parks the 16
 //              indices in the (idle) exchange buffer, from where every thread picks up the
 //              indices of its own pass-0 samples; the phasors are gathered from the table in L2.
-enum { FINE_NONE = 0, FINE_CONST = 1, FINE_WALK = 2 };
+//   FINE_ORBIT the same walking index, evaluated in O(1) per sample from the orbit description of
+//              fine_orbit.h (a kernel parameter): no prefix kernels, no index parking, no extra
+//              barriers, and the programmatic-launch wait can move down to the first flush.  Used
+//              whenever the step has an orbit (all but steps within 2^-5 of an integer); FINE_WALK is
+//              the fallback.
+enum { FINE_NONE = 0, FINE_CONST = 1, FINE_WALK = 2, FINE_ORBIT = 3 };
+
+// the orbit travels as a kernel parameter only in the instantiations that use it
+template <int FINE> struct OrbitArg { };
+template <> struct OrbitArg<FINE_ORBIT> { FineOrbit o; };
 
 // word offset of fine index j inside a window's exchange area: +4 words every 32 so that the
 // 64-byte per-thread chunks are written conflict free with 128-bit stores
@@ -263,7 +273,8 @@ __device__ __forceinline__ int fine_pad_dyn(int j) { return j + 4 * (j >> 5); }
 //        segments (the host requires seg_windows % WPT == 0)
 template <int SF, bool DBG, int FINE, bool MULTI = false>
 __global__ void __launch_bounds__(256, FusedCfg<SF>::CTAS_PER_SM)
-demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_phasor, const SegList<MULTI> segs)
+demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_phasor, const SegList<MULTI> segs,
+                   const OrbitArg<FINE> orb)
 {
     constexpr bool FINE0 = (FINE == FINE_CONST);
     using C = FusedCfg<SF>;
@@ -406,6 +417,8 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
     const uint32_t ga1 = wx + uint32_t(C::pad(lo1 | (hi1 << (B0 + 4)))) * 8u;
     const uint32_t ga2 = wx + uint32_t(C::pad(tL)) * 8u;
 
+    int orbit_j = 0, orbit_r = 0;   // FINE_ORBIT: segment / offset of this thread's current window start
+    bool orbit_init = false;
     uint32_t raw_cnt = 0;           // raw results parked in rawbuf
     uint32_t raw_w0 = tile0 * WPT;  // window index of rawbuf[0]
 
@@ -451,7 +464,29 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             }
 
             // ---- walking fine-tune index: this thread's 16 table indices ---------------------------
-            int fidx[FINE == FINE_WALK ? 16 : 1];
+            int fidx[(FINE == FINE_WALK || FINE == FINE_ORBIT) ? 16 : 1];
+            float2 fph[FINE == FINE_ORBIT ? 16 : 1];
+            if constexpr (FINE == FINE_ORBIT) {
+                // (segment, offset) of this thread's window start: located once, then advanced by the WPT
+                // windows between consecutive tiles of the group; a window that lies inside one
+                // arithmetic progression (all but one in 128/|s|) takes one multiply-add per sample
+                if (!orbit_init) { orbit_locate(orb.o, (unsigned long long)w * N, orbit_j, orbit_r); orbit_init = true; }
+                else orbit_r += WPT * N;
+                (void)orbit_state(orb.o, orbit_j, orbit_r);
+                const int seg_y = orb.o.seg[orbit_j].y, seg_c = orb.o.seg[orbit_j].c, os = orb.o.s;
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+#pragma unroll
+                    for (int c = 0; c < R0; ++c) {
+                        const int il = (E == 1) ? t : ((e >> 1) * 2 * G + 2 * t + (e & 1));
+                        int rr = orbit_r + il + (N / R0) * c;
+                        if (rr <= seg_c) fidx[e * R0 + c] = seg_y - rr * os;
+                        else { int jj = orbit_j; fidx[e * R0 + c] = orbit_state(orb.o, jj, rr); }
+                    }
+                // the phasors do not depend on the IQ tile: gather them (L2) before waiting for it
+#pragma unroll
+                for (int i = 0; i < 16; ++i) fph[i] = __ldg(p.fine + fidx[i]);
+            }
             if constexpr (FINE == FINE_WALK) {
                 group_sync<GROUP>(grp); // the previous tile's gathers from X are done group-wide
                 int x = live ? __ldg(p.fine_x16 + size_t(w) * G + t) : 0;
@@ -557,6 +592,10 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             if constexpr (FINE == FINE_WALK) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) r[i] = pcx_mul(r[i], __ldg(p.fine + fidx[i]));
+            }
+            if constexpr (FINE == FINE_ORBIT) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = pcx_mul(r[i], fph[i]);
             }
             if constexpr (DBG) {
                 if (p.dec && live) {
@@ -791,7 +830,7 @@ inline void fill_pass0_tw(int sf, const float2 *tw_host, Pass0Tw &o)
 
 template <int SF, bool DBG, int FINE, bool MULTI = false>
 cudaError_t launch_fused_v(const DemodParams &p, const Pass0Tw &tw0, float2 phasor, cudaStream_t s, int sm_count,
-                           const SegList<MULTI> &segs = SegList<MULTI>())
+                           const SegList<MULTI> &segs = SegList<MULTI>(), const OrbitArg<FINE> &orb = OrbitArg<FINE>())
 {
     using C = FusedCfg<SF>;
 #ifdef LORAB200_EXP_1CTA   // occupancy experiment: one CTA per SM (tools/build_variant.sh)
@@ -818,14 +857,20 @@ cudaError_t launch_fused_v(const DemodParams &p, const Pass0Tw &tw0, float2 phas
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, demod_fused_kernel<SF, DBG, FINE, MULTI>, p, tw0, phasor, segs);
+    return cudaLaunchKernelEx(&cfg, demod_fused_kernel<SF, DBG, FINE, MULTI>, p, tw0, phasor, segs, orb);
 }
 
 template <int SF>
 cudaError_t launch_fused_sf(const DemodParams &p, const Pass0Tw &tw0, int fine, float2 phasor,
-                            cudaStream_t s, int sm_count)
+                            cudaStream_t s, int sm_count, const FineOrbit *orbit)
 {
     const bool dbg = p.fft != nullptr || p.dec != nullptr;
+    if (fine == FINE_ORBIT) {
+        if (dbg || !orbit) return cudaErrorInvalidValue;
+        OrbitArg<FINE_ORBIT> oa;
+        oa.o = *orbit;
+        return launch_fused_v<SF, false, FINE_ORBIT>(p, tw0, phasor, s, sm_count, SegList<false>(), oa);
+    }
     if (fine == FINE_WALK) return dbg ? cudaErrorInvalidValue : launch_fused_v<SF, false, FINE_WALK>(p, tw0, phasor, s, sm_count);
     if (dbg) return fine == FINE_CONST ? launch_fused_v<SF, true, FINE_CONST>(p, tw0, phasor, s, sm_count)
                                        : launch_fused_v<SF, true, FINE_NONE>(p, tw0, phasor, s, sm_count);
@@ -849,18 +894,18 @@ inline cudaError_t launch_fused_multi(int sf, const DemodParams &p, const Pass0T
     }
 }
 
-// fine: FINE_NONE, FINE_CONST (multiply by `phasor` = fine[idx0], step == 0) or FINE_WALK
-// (p.fine_x16 holds the index at every 16th sample)
+// fine: FINE_NONE, FINE_CONST (multiply by `phasor` = fine[idx0], step == 0), FINE_ORBIT (`orbit`
+// describes the walk) or FINE_WALK (p.fine_x16 holds the index at every 16th sample)
 inline cudaError_t launch_fused(int sf, const DemodParams &p, const Pass0Tw &tw0, int fine, float2 phasor,
-                                cudaStream_t s, int sm_count)
+                                cudaStream_t s, int sm_count, const FineOrbit *orbit = nullptr)
 {
     switch (sf) {
-    case 7: return launch_fused_sf<7>(p, tw0, fine, phasor, s, sm_count);
-    case 8: return launch_fused_sf<8>(p, tw0, fine, phasor, s, sm_count);
-    case 9: return launch_fused_sf<9>(p, tw0, fine, phasor, s, sm_count);
-    case 10: return launch_fused_sf<10>(p, tw0, fine, phasor, s, sm_count);
-    case 11: return launch_fused_sf<11>(p, tw0, fine, phasor, s, sm_count);
-    case 12: return launch_fused_sf<12>(p, tw0, fine, phasor, s, sm_count);
+    case 7: return launch_fused_sf<7>(p, tw0, fine, phasor, s, sm_count, orbit);
+    case 8: return launch_fused_sf<8>(p, tw0, fine, phasor, s, sm_count, orbit);
+    case 9: return launch_fused_sf<9>(p, tw0, fine, phasor, s, sm_count, orbit);
+    case 10: return launch_fused_sf<10>(p, tw0, fine, phasor, s, sm_count, orbit);
+    case 11: return launch_fused_sf<11>(p, tw0, fine, phasor, s, sm_count, orbit);
+    case 12: return launch_fused_sf<12>(p, tw0, fine, phasor, s, sm_count, orbit);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -32,6 +32,7 @@
 #include "mod_synth.cuh"
 #include "decode.cuh"
 #include "rx_kernel.cuh"
+#include "rx_batch.cuh"
 #include "finalize.h"
 #include "tables.h"
 
@@ -164,6 +165,9 @@ struct lorab200_ctx {
     size_t h_raw_cap = 0;
     void *h_stage = nullptr; // pinned staging of small batches (read by the kernel over PCIe)
     size_t h_stage_cap = 0;
+    void *h_rx = nullptr;    // pinned: lorab200_rx_host's state / packets block (read and written by the kernel)
+    size_t h_rx_cap = 0;
+    DevBuf d_rx_iq;          // lorab200_rx_host: the channels' IQ on the device
     // pageable callers (a framework's ordinary port buffers): large H2D copies are staged through
     // a ring of pinned slots so that the PCIe copy of one slot overlaps the memcpy into the next
     void *h_ring = nullptr;
@@ -358,6 +362,19 @@ cudaError_t launch_rx_sf(const RxParams &p, cudaStream_t s, int sm_count)
     return cudaGetLastError();
 }
 
+template <int SF>
+cudaError_t launch_rx_batch_sf(const RxParams &p, const Pass0Tw &tw0, cudaStream_t s, int sm_count)
+{
+    using K = RxBatchCfg<SF>;
+    static SmemAttrOnce attr;
+    if (cudaError_t e = attr.ensure(rx_batch_kernel<SF>, K::SMEM_BYTES); e != cudaSuccess) return e;
+    unsigned grid = p.n_channels;
+    const unsigned cap = unsigned(sm_count) * 8u;   // grid-stride over the channels beyond that
+    if (grid > cap) grid = cap;
+    rx_batch_kernel<SF><<<grid, K::CTA, K::SMEM_BYTES, s>>>(p, tw0);
+    return cudaGetLastError();
+}
+
 bool stream_capturing(cudaStream_t s)
 {
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
@@ -484,13 +501,25 @@ int run_demod(lorab200_ctx *c, const void *iq_dev, size_t n_windows, size_t stri
 
     const bool walk = fine && fine->step != 0.0f;
     if (fine && !walk) p.fine_index0 = fine->index;
+    bool use_fused = false;
+#ifndef LORAB200_NO_FUSED
+    use_fused = !(c->flags & LORAB200_FLAG_SIMPLE_ONLY) && fused_applicable(c->sf, p);
+#endif
+    FineOrbit orbit;
+    bool have_orbit = false;
     if (walk) {
-        // per-chunk index states on the device; the end-of-batch index for the caller in closed
-        // form on the host (fine_walk.h), so this call stays asynchronous
-        int st = fine_prefix(c, fine->index, fine->step, p.fine_len, n_windows, s);
-        if (st) return st;
-        p.fine_x16 = static_cast<const int32_t *>(c->d_fine_x.p);
         const FineWalk fwalk(p.fine_len, fine->step);
+        // The fused kernel evaluates the index in O(1) per sample from the orbit of the walk
+        // (fine_orbit.h) whenever the step has one: nothing to precompute on the device.  Otherwise
+        // (steps within 2^-5 of an integer, the simple kernel): per-chunk index states by pointer
+        // jumping (fine_prefix.cuh).  The end-of-batch index for the caller comes from the closed
+        // form on the host (fine_walk.h) either way, so this call stays asynchronous.
+        have_orbit = use_fused && build_fine_orbit(fwalk, fine->index, orbit);
+        if (!have_orbit) {
+            int st = fine_prefix(c, fine->index, fine->step, p.fine_len, n_windows, s);
+            if (st) return st;
+            p.fine_x16 = static_cast<const int32_t *>(c->d_fine_x.p);
+        }
         fine->index = fwalk.advance(fine->index, uint64_t(n_windows) * c->n);
         // arithmetic-progression fast path of the kernel: an integer step d, or (rounding never carries,
         // Kp == none) every state with k = x - D >= 1 steps by D + 1
@@ -502,7 +531,7 @@ int run_demod(lorab200_ctx *c, const void *iq_dev, size_t n_windows, size_t stri
 
     cudaError_t e;
 #ifndef LORAB200_NO_FUSED
-    if (!(c->flags & LORAB200_FLAG_SIMPLE_ONLY) && fused_applicable(c->sf, p)) {
+    if (use_fused) {
         // fine-tune with a zero step: the index never moves (LoRaDemod.cpp:160 with
         // _finefreqError == 0), so the whole batch is multiplied by one phasor
         float2 phasor = make_float2(1.f, 0.f);
@@ -510,7 +539,8 @@ int run_demod(lorab200_ctx *c, const void *iq_dev, size_t n_windows, size_t stri
             const cfloat f = c->h_table[LORAB200_TABLE_FINE][size_t(fine->index)];
             phasor = make_float2(f.re, f.im);
         }
-        e = launch_fused(c->sf, p, c->tw0, walk ? FINE_WALK : (fine ? FINE_CONST : FINE_NONE), phasor, s, c->sm_count);
+        e = launch_fused(c->sf, p, c->tw0, walk ? (have_orbit ? FINE_ORBIT : FINE_WALK) : (fine ? FINE_CONST : FINE_NONE),
+                         phasor, s, c->sm_count, have_orbit ? &orbit : nullptr);
         c->last_kernel = std::string("fused_sf") + std::to_string(c->sf);
     } else
 #endif
@@ -518,7 +548,7 @@ int run_demod(lorab200_ctx *c, const void *iq_dev, size_t n_windows, size_t stri
         e = launch_simple(c->sf, p, s, c->sm_count);
         c->last_kernel = std::string("simple_sf") + std::to_string(c->sf);
     }
-    if (walk && e == cudaSuccess && !stream_capturing(s)) e = cudaEventRecord(c->fine_done, s);
+    if (walk && !have_orbit && e == cudaSuccess && !stream_capturing(s)) e = cudaEventRecord(c->fine_done, s);
     if (e != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "kernel launch", e);
     c->launches++;
     return LORAB200_OK;
@@ -623,6 +653,8 @@ void lorab200_destroy(lorab200_ctx *c)
     if (c->aux_done) cudaEventDestroy(c->aux_done);
     if (c->h_raw) cudaFreeHost(c->h_raw);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_rx) cudaFreeHost(c->h_rx);
+    if (c->d_rx_iq.p) cudaFree(c->d_rx_iq.p);
     if (c->h_ring) cudaFreeHost(c->h_ring);
     for (auto &ev : c->ring_free) if (ev) cudaEventDestroy(ev);
     (void)cudaGetLastError();
@@ -813,17 +845,96 @@ int lorab200_rx_dev(lorab200_ctx *c, const void *iq_dev, size_t n_channels, size
     p.max_packets = unsigned(max_packets);
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     cudaError_t e;
+    const bool simple = (c->flags & LORAB200_FLAG_SIMPLE_ONLY) != 0;   // the one-window-at-a-time cross-check kernel
     switch (c->sf) {
-    case 7: e = launch_rx_sf<7>(p, s, c->sm_count); break;
-    case 8: e = launch_rx_sf<8>(p, s, c->sm_count); break;
-    case 9: e = launch_rx_sf<9>(p, s, c->sm_count); break;
-    case 10: e = launch_rx_sf<10>(p, s, c->sm_count); break;
-    case 11: e = launch_rx_sf<11>(p, s, c->sm_count); break;
-    default: e = launch_rx_sf<12>(p, s, c->sm_count); break;
+    case 7: e = simple ? launch_rx_sf<7>(p, s, c->sm_count) : launch_rx_batch_sf<7>(p, c->tw0, s, c->sm_count); break;
+    case 8: e = simple ? launch_rx_sf<8>(p, s, c->sm_count) : launch_rx_batch_sf<8>(p, c->tw0, s, c->sm_count); break;
+    case 9: e = simple ? launch_rx_sf<9>(p, s, c->sm_count) : launch_rx_batch_sf<9>(p, c->tw0, s, c->sm_count); break;
+    case 10: e = simple ? launch_rx_sf<10>(p, s, c->sm_count) : launch_rx_batch_sf<10>(p, c->tw0, s, c->sm_count); break;
+    case 11: e = simple ? launch_rx_sf<11>(p, s, c->sm_count) : launch_rx_batch_sf<11>(p, c->tw0, s, c->sm_count); break;
+    default: e = simple ? launch_rx_sf<12>(p, s, c->sm_count) : launch_rx_batch_sf<12>(p, c->tw0, s, c->sm_count); break;
     }
     if (e != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "rx kernel launch", e);
     c->launches++;
-    c->last_kernel = std::string("rx_sf") + std::to_string(c->sf);
+    c->last_kernel = std::string(simple ? "rx_simple_sf" : "rx_sf") + std::to_string(c->sf);
+    return LORAB200_OK;
+}
+
+int lorab200_rx_host(lorab200_ctx *c, const float *const *iq_list, size_t n_channels, size_t n_samples,
+                     unsigned sync, float thresh_db, size_t mtu, lorab200_rx_state *state, int16_t *partial,
+                     int16_t *symbols, lorab200_rx_packet *info, int32_t *n_packets, uint64_t *consumed,
+                     size_t max_packets)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    c->err.clear();
+    if (n_channels == 0) return LORAB200_OK;
+    if (!iq_list || !state || !partial || !symbols || !info || !n_packets || !consumed)
+        return fail(c, LORAB200_ERR_INVALID, "null pointer");
+    if (mtu == 0 || mtu > 32767) return fail(c, LORAB200_ERR_INVALID, "mtu must be 1..32767");
+    if (max_packets == 0 || max_packets > 4096) return fail(c, LORAB200_ERR_INVALID, "max_packets must be 1..4096");
+    if (n_channels > 4096) return fail(c, LORAB200_ERR_UNSUPPORTED, "at most 4096 channels per call");
+    for (size_t ch = 0; ch < n_channels; ++ch)
+        if (!iq_list[ch]) return fail(c, LORAB200_ERR_INVALID, "null channel pointer");
+    CU_TRY(c, cudaSetDevice(c->device));
+    // One pinned block holds everything small that crosses the boundary; the kernel reads and writes
+    // it in place (page-locked memory is device-addressable), so a call is: stage the IQ, one launch,
+    // one synchronise -- no copy calls for state, packets or symbols.
+    const size_t o_state = 0;
+    const size_t o_cons = o_state + ((n_channels * sizeof(lorab200_rx_state) + 15) & ~size_t(15));
+    const size_t o_npk = o_cons + n_channels * sizeof(uint64_t);
+    const size_t o_info = (o_npk + n_channels * sizeof(int32_t) + 15) & ~size_t(15);
+    const size_t o_part = o_info + n_channels * max_packets * sizeof(lorab200_rx_packet);
+    const size_t o_sym = (o_part + n_channels * mtu * sizeof(int16_t) + 15) & ~size_t(15);
+    const size_t total = o_sym + n_channels * max_packets * mtu * sizeof(int16_t);
+    int st;
+    if ((st = ensure_pinned(c, c->h_rx, c->h_rx_cap, total))) return st;
+    char *hb = static_cast<char *>(c->h_rx);
+    std::memcpy(hb + o_state, state, n_channels * sizeof(lorab200_rx_state));
+    std::memcpy(hb + o_part, partial, n_channels * mtu * sizeof(int16_t));
+    const size_t stride = (n_samples + 1) & ~size_t(1);                 // keep every channel 16-byte aligned
+    if ((st = ensure_dev(c, c->d_rx_iq, n_channels * stride * sizeof(float2)))) return st;
+    float2 *d_iq = static_cast<float2 *>(c->d_rx_iq.p);
+    for (size_t ch = 0; ch < n_channels; ++ch)
+        if ((st = h2d_copy(c, d_iq + ch * stride, iq_list[ch], n_samples * sizeof(float2), c->stream, is_pageable(iq_list[ch]))))
+            { cudaStreamSynchronize(c->stream); return st; }
+    st = lorab200_rx_dev(c, d_iq, n_channels, stride, n_samples, sync, thresh_db, mtu,
+                         reinterpret_cast<lorab200_rx_state *>(hb + o_state), reinterpret_cast<int16_t *>(hb + o_part),
+                         reinterpret_cast<int16_t *>(hb + o_sym), reinterpret_cast<lorab200_rx_packet *>(hb + o_info),
+                         reinterpret_cast<int32_t *>(hb + o_npk), reinterpret_cast<uint64_t *>(hb + o_cons),
+                         max_packets, c->stream);
+    if (st) { cudaStreamSynchronize(c->stream); return st; }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(state, hb + o_state, n_channels * sizeof(lorab200_rx_state));
+    std::memcpy(partial, hb + o_part, n_channels * mtu * sizeof(int16_t));
+    std::memcpy(consumed, hb + o_cons, n_channels * sizeof(uint64_t));
+    std::memcpy(n_packets, hb + o_npk, n_channels * sizeof(int32_t));
+    std::memcpy(info, hb + o_info, n_channels * max_packets * sizeof(lorab200_rx_packet));
+    // the "power" / "snr" signals with the host libm (LoRaDetector.hpp:50-54, LoRaDemod.cpp:173): the
+    // reference's own bits, from the raw peak and total the kernel kept for the DOWNCHIRP1 window
+    auto host_db = [&](float max_mag2, double total, float &power, float &snr) {
+        RawResultHost rr{};
+        rr.max_mag2 = max_mag2;
+        rr.total = total;
+        lorab200_result o;
+        finalize_host(&rr, 1, c->pscale, &o);
+        power = o.power;
+        snr = o.power - o.power_avg;
+    };
+    for (size_t ch = 0; ch < n_channels; ++ch) {
+        const size_t np = size_t(n_packets[ch] < 0 ? 0 : n_packets[ch]);
+        for (size_t q = 0; q < np; ++q) {
+            lorab200_rx_packet &pk = info[ch * max_packets + q];
+            host_db(pk.max_mag2, pk.total, pk.power, pk.snr);
+        }
+        if (state[ch].phase == RX_QUARTERCHIRP || state[ch].phase == RX_DATASYMBOLS)
+            host_db(state[ch].sig_max_mag2, state[ch].sig_total, state[ch].sig_power, state[ch].sig_snr);
+    }
+    // only the packets that were written (the rest of the slots is scratch)
+    for (size_t ch = 0; ch < n_channels; ++ch) {
+        const size_t np = size_t(n_packets[ch] < 0 ? 0 : n_packets[ch]);
+        if (np) std::memcpy(symbols + ch * max_packets * mtu, hb + o_sym + ch * max_packets * mtu * sizeof(int16_t),
+                            np * mtu * sizeof(int16_t));
+    }
     return LORAB200_OK;
 }
 

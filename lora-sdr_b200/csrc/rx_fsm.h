@@ -41,6 +41,10 @@ struct RxState {
     // signals emitted at DOWNCHIRP1 for the packet being received (LoRaDemod.cpp:267-269)
     int32_t sig_error;
     float   sig_power, sig_snr;
+    // raw detector outputs of that DOWNCHIRP1 window (set by the receiver kernels, not by rx_step):
+    // a host can redo the dB conversions with its own libm and get the reference's bits
+    float   sig_max_mag2, sig_reserved;
+    double  sig_total;
 };
 
 // what one transition asks the caller to do
@@ -54,6 +58,7 @@ LB_RX_HD void rx_reset(RxState &s)
 {
     s.phase = RX_FRAMESYNC; s.table = LORAB200_TABLE_UP; s.sym_count = 0; s.prev_value = 0; s.freq_error = 0;
     s.fine_index = 0; s.ffe = 0.0f; s.sig_error = 0; s.sig_power = 0.0f; s.sig_snr = 0.0f;
+    s.sig_max_mag2 = 0.0f; s.sig_reserved = 0.0f; s.sig_total = 0.0;
 }
 
 // LoRaDemod.cpp:181-189: in FRAMESYNC a window that looks like sync word 0 needs the next

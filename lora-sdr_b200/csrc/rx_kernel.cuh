@@ -17,6 +17,8 @@ struct RxPacketInfo {
     int32_t length;     // symbols in the packet
     int32_t error;      // the "error" signal (LoRaDemod.cpp:267)
     float power, snr;   // the "power" / "snr" signals (:268-269)
+    float max_mag2, reserved;   // raw detector outputs behind them
+    double total;
 };
 
 struct RxParams {
@@ -79,6 +81,8 @@ __global__ void __launch_bounds__(kSimpleThreads) rx_kernel(const RxParams p)
     __shared__ RxState st;
     __shared__ FineWalkDev fw;
     __shared__ lorab200_result res[2];
+    __shared__ float raw_max0;
+    __shared__ double raw_total0;
     __shared__ unsigned long long off;
     __shared__ int go, need2, idx_after[2], walk_now, npk;
 
@@ -118,12 +122,13 @@ __global__ void __launch_bounds__(kSimpleThreads) rx_kernel(const RxParams p)
                                                         p.tw, nullptr, nullptr, F, s_val, s_idx, s_sum);
                 if (tid == 0) {
                     finalize_device(raw, p.power_scale, &res[w]);
-                    if (w == 0) need2 = rx_needs_second(p.cfg, st, res[0]) ? 1 : 0;
+                    if (w == 0) { need2 = rx_needs_second(p.cfg, st, res[0]) ? 1 : 0; raw_max0 = raw.max_mag2; raw_total0 = raw.total; }
                 }
                 __syncthreads();
                 if (w == 0 && !need2) break;
             }
             if (tid == 0) {
+                if (st.phase == RX_DOWNCHIRP1) { st.sig_max_mag2 = raw_max0; st.sig_total = raw_total0; }
                 const RxAction a = rx_step(p.cfg, st, res[0], idx_after[0], need2 != 0, res[1]);
                 if (a.emit_symbol >= 0 && st.sym_count >= 1 && st.sym_count <= p.cfg.mtu)   // (sym_count already incremented)
                     slots[size_t(npk) * p.cfg.mtu + (st.sym_count - 1)] = int16_t(a.emit_symbol);
@@ -132,6 +137,9 @@ __global__ void __launch_bounds__(kSimpleThreads) rx_kernel(const RxParams p)
                     info[npk].error = st.sig_error;
                     info[npk].power = st.sig_power;
                     info[npk].snr = st.sig_snr;
+                    info[npk].max_mag2 = st.sig_max_mag2;
+                    info[npk].reserved = 0.0f;
+                    info[npk].total = st.sig_total;
                     npk++;
                 }
                 off += a.consume;
@@ -141,6 +149,8 @@ __global__ void __launch_bounds__(kSimpleThreads) rx_kernel(const RxParams p)
         // park the packet under construction for the next call, write the state back
         if (st.phase == RX_DATASYMBOLS && unsigned(npk) < p.max_packets)
             for (int k = tid; k < st.sym_count; k += T) p.partial[size_t(ch) * p.cfg.mtu + k] = slots[size_t(npk) * p.cfg.mtu + k];
+        // slots that hold no packet read as empty (a consumer may scan all max_packets entries)
+        for (unsigned q = unsigned(npk) + tid; q < p.max_packets; q += T) info[q].length = 0;
         if (tid == 0) { p.state[ch] = st; p.n_packets[ch] = npk; p.consumed[ch] = off; }
         __syncthreads();
     }

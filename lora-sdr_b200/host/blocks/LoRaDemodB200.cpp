@@ -25,7 +25,12 @@
 //   * work() may consume many windows per call; debug ports then carry the concatenation
 //     of what the reference would have produced over the same number of calls;
 //   * two extra setters: setDebugPorts(bool) (default true; false skips the raw/dec/fft
-//     dumps and their D2H traffic) and setMaxBatch(n).
+//     dumps and their D2H traffic) and setMaxBatch(n);
+//   * with the debug ports off, work() does not walk windows on the host at all: it hands the
+//     whole input buffer to the on-device receiver (lorab200_rx_host -> rx_batch.cuh: the same
+//     state machine, one launch per work() call, speculative batches of windows), posts the
+//     packets it returns and consumes what it consumed.  The state it carries between calls is
+//     this block's _st.  setDeviceReceiver(false) keeps the host walk (this file's original path).
 //
 // Builds against <Pothos/Framework.hpp> -- the real one, or ministream's stand-in.
 #include <Pothos/Framework.hpp>
@@ -99,6 +104,7 @@ public:
         _thresh(-30.0f),
         _mtu(256),
         _debugPorts(true),
+        _deviceReceiver(true),
         _maxBatch(4096)
     {
         lorab200::rx_reset(_st);
@@ -107,6 +113,7 @@ public:
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, setMTU));
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, setDebugPorts));
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, setMaxBatch));
+        this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, setDeviceReceiver));
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, getKernelLaunches));
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, getDemodCalls));
         this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodB200, getDemodWindows));
@@ -152,6 +159,7 @@ public:
     void setMTU(const size_t mtu) { _mtu = mtu; }
     void setDebugPorts(const bool enable) { _debugPorts = enable; }
     void setMaxBatch(const size_t n) { _maxBatch = std::max<size_t>(1, n); }
+    void setDeviceReceiver(const bool enable) { _deviceReceiver = enable; }
     unsigned long long getKernelLaunches(void) const { return lorab200_kernel_launches(_ctx); }
     unsigned long long getDemodCalls(void) const { return _demodCalls; } // lorab200_demod_host calls so far
     unsigned long long getDemodWindows(void) const { return _demodWindows; } // windows submitted (incl. unused speculation)
@@ -159,10 +167,69 @@ public:
     void activate(void)
     {
         lorab200::rx_reset(_st);
+        _sigEmitted = false;
+    }
+
+    //! debug ports off: the whole input buffer goes through the on-device receiver in one call
+    void workReceiver(void)
+    {
+        auto inPort = this->input(0);
+        const size_t avail = inPort->elements();
+        if (avail < N*2) return;
+        const float *iq = reinterpret_cast<const float *>(inPort->buffer().as<const std::complex<float> *>());
+        const size_t n = std::min(avail, _maxBatch*N);
+        if (_rxMtu != _mtu)
+        {
+            //setMTU between packets: re-shape the scratch (a packet under construction keeps its symbols)
+            _rxPartial.resize(_mtu, 0);
+            _rxSymbols.assign(size_t(kRxMaxPackets)*_mtu, 0);
+            _rxMtu = _mtu;
+        }
+        static_assert(sizeof(lorab200_rx_state) == sizeof(lorab200::RxState), "the C struct mirrors RxState");
+        lorab200_rx_state st;
+        std::memcpy(&st, &_st, sizeof(st));
+        lorab200_rx_packet info[kRxMaxPackets];
+        int32_t npk = 0;
+        uint64_t consumed = 0;
+        ++_demodCalls;
+        _demodWindows += n/N;
+        const int rc = lorab200_rx_host(_ctx, &iq, 1, n, _sync, _thresh, _mtu, &st, _rxPartial.data(),
+            _rxSymbols.data(), info, &npk, &consumed, kRxMaxPackets);
+        if (rc != LORAB200_OK)
+        {
+            throw Pothos::Exception("LoRaDemodB200::work()", std::string(lorab200_strerror(rc)) + ": " + lorab200_last_error(_ctx));
+        }
+        std::memcpy(&_st, &st, sizeof(st));
+        for (int32_t p = 0; p < npk; p++)
+        {
+            //the signals belong to the packet's DOWNCHIRP1 window (LoRaDemod.cpp:267-269): emitted when that
+            //window is passed -- at the end of an earlier call for a packet that was still being received
+            if (not (p == 0 and _sigEmitted))
+            {
+                this->emitSignal("error", int(info[p].error));
+                this->emitSignal("power", info[p].power);
+                this->emitSignal("snr", info[p].snr);
+            }
+            _sigEmitted = false;
+            Pothos::Packet pkt;
+            pkt.payload = Pothos::BufferChunk(typeid(int16_t), _mtu);
+            std::memcpy(pkt.payload.as<int16_t *>(), _rxSymbols.data() + size_t(p)*_mtu, size_t(info[p].length)*sizeof(int16_t));
+            pkt.payload.length = size_t(info[p].length)*sizeof(int16_t);
+            this->output(0)->postMessage(pkt);
+        }
+        if ((_st.phase == lorab200::RX_QUARTERCHIRP or _st.phase == lorab200::RX_DATASYMBOLS) and not _sigEmitted)
+        {
+            this->emitSignal("error", int(_st.sig_error));
+            this->emitSignal("power", _st.sig_power);
+            this->emitSignal("snr", _st.sig_snr);
+            _sigEmitted = true;
+        }
+        inPort->consume(size_t(consumed));
     }
 
     void work(void)
     {
+        if (not _debugPorts and _deviceReceiver) return this->workReceiver();
         auto inPort = this->input(0);
         const size_t avail = inPort->elements();
         if (avail < N*2) return;
@@ -296,7 +363,7 @@ public:
     }
 
 private:
-    enum { kDebugWindows = 64, kIdleSpecMin = 16 };
+    enum { kDebugWindows = 64, kIdleSpecMin = 16, kRxMaxPackets = 16 };
 
     struct Window
     {
@@ -428,7 +495,12 @@ private:
     float _thresh;
     size_t _mtu;
     bool _debugPorts;
+    bool _deviceReceiver;
     size_t _maxBatch;
+    //device-receiver path: scratch between calls (the packet under construction, returned packets)
+    std::vector<int16_t> _rxPartial, _rxSymbols;
+    size_t _rxMtu = 0;
+    bool _sigEmitted = false;               //the signals of the packet under construction are out already
     Pothos::OutputPort *_rawPort;
     Pothos::OutputPort *_decPort;
     Pothos::OutputPort *_fftPort;

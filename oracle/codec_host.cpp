@@ -60,3 +60,18 @@ extern "C" void rx_host_step(const int32_t *cfg4, void *state, const lorab200_re
                                                    have_r1 != 0, *r1);
     out3[0] = a.consume; out3[1] = a.emit_symbol; out3[2] = a.post_packet;
 }
+
+/* ---- the fine-tune index orbit (lora-sdr_b200/csrc/fine_orbit.h), host build, for tests ---------- */
+#include "../lora-sdr_b200/csrc/fine_orbit.h"
+#include "../lora-sdr_b200/csrc/fine_walk.cpp"
+
+/* builds the orbit of (len, d, x0); returns n_seg (0 = no orbit) and evaluates it at the n_q sample numbers q[] */
+extern "C" int fine_orbit_host(int32_t len, float d, int32_t x0, const uint64_t *q, int n_q, int32_t *out, int64_t *info3)
+{
+    const lorab200::FineWalk fw(len, d);
+    lorab200::FineOrbit o;
+    if (!lorab200::build_fine_orbit(fw, x0, o)) return 0;
+    for (int i = 0; i < n_q; ++i) out[i] = lorab200::orbit_at(o, q[i]);
+    if (info3) { info3[0] = o.n_pre; info3[1] = o.pre_len; info3[2] = o.period; }
+    return o.n_seg;
+}

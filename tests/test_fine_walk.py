@@ -79,3 +79,70 @@ def test_bad_arguments(lib):
         lib.fine_advance(7, 0, 1e9, 10)
     with pytest.raises(lib.Lorab200Error):
         lib.fine_advance(6, 0, 1.0, 10)
+
+
+# ---- fine_orbit.h: the walk as segments + one period (what the fused kernel evaluates in O(1)) ----------
+
+def _orbit_lib():
+    import ctypes as C
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    subprocess.run(["make", "-C", str(root / "oracle"), "libcodec_host.so"], check=True, capture_output=True)
+    L = C.CDLL(str(root / "oracle" / "libcodec_host.so"))
+    L.fine_orbit_host.argtypes = [C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    return L
+
+
+def _orbit(L, length, d32, x0, q):
+    import ctypes as C
+    q = np.ascontiguousarray(q, np.uint64)
+    out = np.zeros(q.size, np.int32)
+    info = np.zeros(3, np.int64)
+    n_seg = L.fine_orbit_host(length, C.c_float(d32), x0, q.ctypes.data_as(C.c_void_p), q.size,
+                              out.ctypes.data_as(C.c_void_p), info.ctypes.data_as(C.c_void_p))
+    return n_seg, out, info
+
+
+@pytest.mark.parametrize("sf", [7, 9, 12])
+def test_orbit_equals_sequential_walk(lib, oracle, sf):
+    """Every sample of a walk a few wraps long (SF7/9; bounded so the Python walk stays cheap), and
+    random far-away samples against the closed-form advance (itself tested against the walk above),
+    for every step in STEPS that has an orbit."""
+    L = _orbit_lib()
+    n = 1 << sf
+    length = n * 128
+    rng = np.random.default_rng(sf)
+    have = 0
+    for d in STEPS + [13.37, 2.5, -2.5, 14.0, 127.0]:
+        if d == 0.0 or abs(d) >= length:
+            continue
+        d32 = float(np.float32(d))
+        for x0 in [0, 5, length - 1] + [int(v) for v in rng.integers(0, length, size=2)]:
+            total = int(min(40000, max(3 * n, 3.3 * length / max(abs(d), 1.0)))) if sf < 12 else 2 * n
+            q = np.arange(total, dtype=np.uint64)
+            n_seg, got, info = _orbit(L, length, d32, x0, q)
+            if n_seg == 0:
+                continue
+            have += 1
+            x, want = x0, np.empty(total, np.int32)
+            for i in range(total):
+                want[i] = x
+                x = oracle.fine_next(x, d32, length)
+            assert np.array_equal(got, want), (sf, d, x0, int(np.argmax(got != want)), info)
+            far = np.concatenate([rng.integers(0, 40 * length, size=24), [10**7 + 3, 2**33 + 12345]]).astype(np.uint64)
+            _, g, _ = _orbit(L, length, d32, x0, far)
+            for k, big in enumerate(far):
+                assert int(g[k]) == lib.fine_advance(sf, x0, d32, int(big)), (sf, d, x0, int(big))
+    assert have >= 40
+
+
+def test_orbit_refuses_what_it_cannot_describe(lib):
+    L = _orbit_lib()
+    length = 128 * 128
+    for d in (3.0001, 2.00001, 7.000001):             # finite carry threshold inside the table
+        n_seg, _, _ = _orbit(L, length, float(np.float32(d)), 77, np.zeros(1, np.uint64))
+        assert n_seg == 0, d
+    for d in (-0.5, -1e-3):                           # D + 1 == 0: the index never moves (caller's constant path)
+        n_seg, _, _ = _orbit(L, length, float(np.float32(d)), 77, np.zeros(1, np.uint64))
+        assert n_seg == 0, d

@@ -37,16 +37,23 @@ def _unpack(r, c):
 
 
 @needs_chain
-@pytest.mark.parametrize("sf,thresh", [(7, -30.0), (7, -4.0), (8, -30.0), (9, -30.0), (10, -4.0), (12, -30.0)])
-def test_rx_dev_matches_the_reference_block(lib, cuda_ok, sf, thresh):
+@pytest.mark.parametrize("flags", [0, 1], ids=["batch", "simple"])
+@pytest.mark.parametrize("sf,thresh", [(7, -30.0), (7, -4.0), (8, -30.0), (9, -30.0), (10, -4.0), (11, -30.0), (12, -30.0), (12, -4.0)])
+def test_rx_dev_matches_the_reference_block(lib, cuda_ok, sf, thresh, flags):
+    """flags 0: the speculative-batch receiver (rx_batch.cuh); 1 = LORAB200_FLAG_SIMPLE_ONLY: the
+    one-window-at-a-time receiver (rx_kernel.cuh) kept as the cross-check."""
     import torch
     rng = np.random.default_rng(sf * 7 + int(-thresh))
     nch, mtu = 5, 96
     buf = _streams(sf, nch, rng, sigma=0.05)
-    d = lib.Demod(sf)
+    d = lib.Demod(sf, flags=flags)
     r = d.rx_dev(torch.from_numpy(buf).cuda(), thresh=thresh, mtu=mtu, max_packets=12)
     torch.cuda.synchronize()
-    assert d.last_kernel.startswith("rx_sf")
+    assert d.last_kernel.startswith("rx_simple_sf" if flags else "rx_sf")
+    # slots that hold no packet read as empty
+    info_all = r["info"].cpu().numpy()
+    for c in range(nch):
+        assert np.all(info_all[c, int(r["n_packets"][c]):, 0] == 0)
     total_packets = 0
     for c in range(nch):
         ref = loopback.receive(sf, 4, buf[c], use_b200=False, debug_ports=True, mtu=mtu, thresh=thresh)
@@ -101,4 +108,47 @@ def test_iq_to_payload_bytes_entirely_on_the_device(lib, cuda_ok, sf):
         assert got == ref["decoded"], f"channel {c}"
         n_bytes += sum(len(g) for g in got)
     assert n_bytes > 0
+    d.close()
+
+
+@needs_chain
+@pytest.mark.parametrize("sf,thresh", [(7, -30.0), (9, -4.0), (12, -30.0)])
+def test_rx_host_is_bit_identical_to_the_reference_block(lib, cuda_ok, sf, thresh):
+    """lorab200_rx_host (what the block's work() calls): host buffers, several channels per call, fed
+    in pieces with the unconsumed tail re-presented; packets, symbols, the error signal, the samples
+    consumed AND the power signal (recomputed with the host libm from the raw peak / total) equal the
+    unmodified reference block's, bit for bit."""
+    rng = np.random.default_rng(900 + sf)
+    nch, mtu = 3, 96
+    buf = _streams(sf, nch, rng, sigma=0.05)
+    d = lib.Demod(sf)
+    n = 1 << sf
+    piece = 11 * n + 7
+    for c in range(nch):
+        ref = loopback.receive(sf, 4, buf[c], use_b200=False, debug_ports=True, mtu=mtu, thresh=thresh)
+        got, state, pos, pending = [], None, 0, np.zeros(0, np.complex64)
+        stream = buf[c]
+        used_total = 0
+        while pos < stream.size or pending.size >= 2 * n:
+            pending = np.concatenate([pending, stream[pos:pos + piece]])
+            pos += piece
+            if pending.size < 2 * n:
+                continue
+            r = d.rx_host([pending], thresh=thresh, mtu=mtu, max_packets=4, state=state)
+            state = r["state"]
+            for p in range(int(r["n_packets"][0])):
+                info = r["info"][0, p]
+                got.append(dict(symbols=r["symbols"][0, p, : info[0]].copy(), error=int(info[1]),
+                                power=float(info[2:3].view(np.float32)[0])))
+            used = int(r["consumed"][0])
+            used_total += used
+            pending = pending[used:]
+            if used == 0 and pos >= stream.size:
+                break
+        assert len(got) == len(ref["symbols"]), f"channel {c}: {len(got)} packets vs {len(ref['symbols'])}"
+        for p, g in enumerate(got):
+            assert np.array_equal(g["symbols"], ref["symbols"][p])
+            assert g["error"] == ref["error"][p]
+            assert g["power"] == ref["power"][p], "power signal not bit-identical"
+        assert used_total == ref["samples"]
     d.close()

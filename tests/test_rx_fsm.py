@@ -22,7 +22,7 @@ def run_fsm(L, oracle, tables, sf, iq, sync, thresh, mtu):
     n = 1 << sf
     up, down, fine = tables
     cfg = (C.c_int32 * 4)(n, sync, mtu, int(np.float32(thresh).view(np.int32)))
-    state = (C.c_int32 * 10)()                         # all zero = activate()
+    state = (C.c_int32 * 14)()                         # all zero = activate()
     L.rx_host_needs_second.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.rx_host_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     off, packets, errors, cur = 0, [], [], []
