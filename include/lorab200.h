@@ -204,6 +204,11 @@ int lorab200_demod_host(lorab200_ctx *ctx, const float *iq, size_t n_windows,
  * pinned memory lets the H2D/D2H copies run at full PCIe rate.  NULL on failure. */
 void *lorab200_alloc_pinned(size_t bytes);
 void lorab200_free_pinned(void *p);
+/* 1 when p points into page-locked (or device) memory, 0 for ordinary pageable memory: which of the
+ * two host-buffer paths a call with this pointer takes.  A block whose input BufferManager hands out
+ * lorab200_alloc_pinned slabs (LoRaDemod.cpp:348-358 is where the reference picks its manager) gets
+ * the direct copy. */
+int lorab200_is_pinned(const void *p);
 
 /* Pack results into the wire format of the demod's output packet: one int16
  * per symbol (LoRaDemod.cpp:260,290: _outSymbols.as<int16_t*>()[n] = int16_t(value)). */
@@ -355,6 +360,21 @@ int lorab200_encode_dev(lorab200_ctx *ctx, const uint8_t *payloads_dev, size_t n
                         size_t symbols_stride, int32_t *n_symbols_dev, void *cuda_stream);
 
 /* ---- diagnostics ----------------------------------------------------------- */
+
+/*
+ * Host-buffer twins of lorab200_encode_dev / lorab200_decode_dev / lorab200_mod_dev: the same
+ * arguments with every array in HOST memory (pageable is fine: a batch is a handful of packets),
+ * synchronous.  They are what the /lora/lora_encoder, /lora/lora_decoder and /lora/lora_mod block
+ * shells call from work() (LoRaEncoder.cpp:137-228, LoRaDecoder.cpp:196-397, LoRaMod.cpp:120-229).
+ */
+int lorab200_encode_host(lorab200_ctx *ctx, const uint8_t *payloads, size_t n_packets, size_t payload_stride,
+                         const int32_t *lengths, const lorab200_encoder_cfg *cfg, uint16_t *symbols,
+                         size_t symbols_stride, int32_t *n_symbols);
+int lorab200_decode_host(lorab200_ctx *ctx, const uint16_t *symbols, size_t n_packets, size_t symbols_stride,
+                         const int32_t *n_symbols, const lorab200_decoder_cfg *cfg, uint8_t *bytes,
+                         size_t bytes_stride, int32_t *lengths);
+int lorab200_mod_host(lorab200_ctx *ctx, const uint16_t *symbols, size_t n_packets, size_t syms_per_packet,
+                      unsigned sync, size_t padding, float ampl, int ovs, int mode, float *iq);
 
 const char *lorab200_strerror(int status);
 const char *lorab200_last_error(const lorab200_ctx *ctx); /* "" if none; ctx may be NULL for create errors */

@@ -51,8 +51,8 @@ EXPORTS = [
     "lorab200_table_dev", "lorab200_set_table", "lorab200_tables_sync_from_dev",
     "lorab200_gen_chirp", "lorab200_demod_dev", "lorab200_demod_host", "lorab200_pack_symbols",
     "lorab200_kernel_launches", "lorab200_last_kernel", "lorab200_alloc_pinned",
-    "lorab200_free_pinned", "lorab200_table_len", "lorab200_build_table", "lorab200_fine_advance",
-    "lorab200_demod_multi_dev", "lorab200_mod_samples", "lorab200_mod_dev", "lorab200_decode_dev", "lorab200_rx_dev", "lorab200_rx_host", "lorab200_encode_dev", "lorab200_encode_symbols",
+    "lorab200_free_pinned", "lorab200_is_pinned", "lorab200_table_len", "lorab200_build_table", "lorab200_fine_advance",
+    "lorab200_demod_multi_dev", "lorab200_mod_samples", "lorab200_mod_dev", "lorab200_decode_dev", "lorab200_rx_dev", "lorab200_rx_host", "lorab200_encode_host", "lorab200_decode_host", "lorab200_mod_host", "lorab200_encode_dev", "lorab200_encode_symbols",
 ]
 
 
@@ -161,6 +161,7 @@ def load_library() -> C.CDLL:
     L.lorab200_alloc_pinned.restype = vp
     L.lorab200_free_pinned.argtypes = [vp]
     L.lorab200_free_pinned.restype = None
+    L.lorab200_is_pinned.argtypes = [vp]
     _lib = L
     return L
 

@@ -168,6 +168,7 @@ struct lorab200_ctx {
     void *h_rx = nullptr;    // pinned: lorab200_rx_host's state / packets block (read and written by the kernel)
     size_t h_rx_cap = 0;
     DevBuf d_rx_iq;          // lorab200_rx_host: the channels' IQ on the device
+    DevBuf d_hio[4];         // host-buffer twins of encode / decode / mod: inputs and outputs on the device
     // pageable callers (a framework's ordinary port buffers): large H2D copies are staged through
     // a ring of pinned slots so that the PCIe copy of one slot overlaps the memcpy into the next
     void *h_ring = nullptr;
@@ -655,6 +656,7 @@ void lorab200_destroy(lorab200_ctx *c)
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_rx) cudaFreeHost(c->h_rx);
     if (c->d_rx_iq.p) cudaFree(c->d_rx_iq.p);
+    for (DevBuf &b : c->d_hio) if (b.p) cudaFree(b.p);
     if (c->h_ring) cudaFreeHost(c->h_ring);
     for (auto &ev : c->ring_free) if (ev) cudaEventDestroy(ev);
     (void)cudaGetLastError();
@@ -1232,6 +1234,86 @@ void *lorab200_alloc_pinned(size_t bytes)
 void lorab200_free_pinned(void *p)
 {
     if (p) cudaFreeHost(p);
+}
+
+// ---- host-buffer twins of the packet-level entry points: what a block's work() calls ---------------
+// (stage the batch, one launch, copy the results back, synchronise; the batch is a handful of packets)
+
+int lorab200_encode_host(lorab200_ctx *c, const uint8_t *payloads, size_t n_packets, size_t payload_stride,
+                         const int32_t *lengths, const lorab200_encoder_cfg *cfg, uint16_t *symbols,
+                         size_t symbols_stride, int32_t *n_symbols)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    c->err.clear();
+    if (n_packets == 0) return LORAB200_OK;
+    if (!payloads || !cfg || !symbols || !n_symbols) return fail(c, LORAB200_ERR_INVALID, "null pointer");
+    CU_TRY(c, cudaSetDevice(c->device));
+    int st;
+    const size_t pb = n_packets * payload_stride, sb = n_packets * symbols_stride * sizeof(uint16_t), lb = n_packets * sizeof(int32_t);
+    if ((st = ensure_dev(c, c->d_hio[0], pb)) || (st = ensure_dev(c, c->d_hio[1], lb)) ||
+        (st = ensure_dev(c, c->d_hio[2], sb)) || (st = ensure_dev(c, c->d_hio[3], lb))) return st;
+    CU_TRY(c, cudaMemcpyAsync(c->d_hio[0].p, payloads, pb, cudaMemcpyHostToDevice, c->stream));
+    if (lengths) CU_TRY(c, cudaMemcpyAsync(c->d_hio[1].p, lengths, lb, cudaMemcpyHostToDevice, c->stream));
+    st = lorab200_encode_dev(c, static_cast<const uint8_t *>(c->d_hio[0].p), n_packets, payload_stride,
+                             lengths ? static_cast<const int32_t *>(c->d_hio[1].p) : nullptr, cfg,
+                             static_cast<uint16_t *>(c->d_hio[2].p), symbols_stride, static_cast<int32_t *>(c->d_hio[3].p), c->stream);
+    if (st) { cudaStreamSynchronize(c->stream); return st; }
+    CU_TRY(c, cudaMemcpyAsync(symbols, c->d_hio[2].p, sb, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(n_symbols, c->d_hio[3].p, lb, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return LORAB200_OK;
+}
+
+int lorab200_decode_host(lorab200_ctx *c, const uint16_t *symbols, size_t n_packets, size_t symbols_stride,
+                         const int32_t *n_symbols, const lorab200_decoder_cfg *cfg, uint8_t *bytes,
+                         size_t bytes_stride, int32_t *lengths)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    c->err.clear();
+    if (n_packets == 0) return LORAB200_OK;
+    if (!symbols || !cfg || !bytes || !lengths) return fail(c, LORAB200_ERR_INVALID, "null pointer");
+    CU_TRY(c, cudaSetDevice(c->device));
+    int st;
+    const size_t sb = n_packets * symbols_stride * sizeof(uint16_t), bb = n_packets * bytes_stride, lb = n_packets * sizeof(int32_t);
+    if ((st = ensure_dev(c, c->d_hio[0], sb)) || (st = ensure_dev(c, c->d_hio[1], lb)) ||
+        (st = ensure_dev(c, c->d_hio[2], bb)) || (st = ensure_dev(c, c->d_hio[3], lb))) return st;
+    CU_TRY(c, cudaMemcpyAsync(c->d_hio[0].p, symbols, sb, cudaMemcpyHostToDevice, c->stream));
+    if (n_symbols) CU_TRY(c, cudaMemcpyAsync(c->d_hio[1].p, n_symbols, lb, cudaMemcpyHostToDevice, c->stream));
+    st = lorab200_decode_dev(c, static_cast<const uint16_t *>(c->d_hio[0].p), n_packets, symbols_stride,
+                             n_symbols ? static_cast<const int32_t *>(c->d_hio[1].p) : nullptr, cfg,
+                             static_cast<uint8_t *>(c->d_hio[2].p), bytes_stride, static_cast<int32_t *>(c->d_hio[3].p), c->stream);
+    if (st) { cudaStreamSynchronize(c->stream); return st; }
+    CU_TRY(c, cudaMemcpyAsync(bytes, c->d_hio[2].p, bb, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(lengths, c->d_hio[3].p, lb, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return LORAB200_OK;
+}
+
+int lorab200_mod_host(lorab200_ctx *c, const uint16_t *symbols, size_t n_packets, size_t syms_per_packet, unsigned sync,
+                      size_t padding, float ampl, int ovs, int mode, float *iq)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    c->err.clear();
+    if (n_packets == 0) return LORAB200_OK;
+    if (!iq || (!symbols && syms_per_packet)) return fail(c, LORAB200_ERR_INVALID, "symbols / iq is null");
+    if (ovs < 1 || ovs > 256) return fail(c, LORAB200_ERR_INVALID, "ovs must be in 1..256 (LoRaMod::setOvs)");
+    CU_TRY(c, cudaSetDevice(c->device));
+    int st;
+    const size_t per = lorab200_mod_samples(c->sf, ovs, syms_per_packet, padding);
+    const size_t sb = n_packets * (syms_per_packet ? syms_per_packet : 1) * sizeof(uint16_t), qb = n_packets * per * sizeof(float2);
+    if ((st = ensure_dev(c, c->d_hio[0], sb)) || (st = ensure_dev(c, c->d_hio[2], qb))) return st;
+    if (syms_per_packet) CU_TRY(c, cudaMemcpyAsync(c->d_hio[0].p, symbols, n_packets * syms_per_packet * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    st = lorab200_mod_dev(c, static_cast<const uint16_t *>(c->d_hio[0].p), n_packets, syms_per_packet, sync, padding, ampl, ovs,
+                          mode, c->d_hio[2].p, c->stream);
+    if (st) { cudaStreamSynchronize(c->stream); return st; }
+    CU_TRY(c, cudaMemcpyAsync(iq, c->d_hio[2].p, qb, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return LORAB200_OK;
+}
+
+int lorab200_is_pinned(const void *p)
+{
+    return (p && !is_pageable(p)) ? 1 : 0;
 }
 
 void lorab200_pack_symbols(const lorab200_result *results, size_t n, int16_t *symbols)

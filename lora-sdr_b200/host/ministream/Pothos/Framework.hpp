@@ -15,6 +15,7 @@
 #pragma once
 #include <complex>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -176,12 +177,20 @@ struct BufferManagerArgs {
 class BufferManager {
 public:
     typedef std::shared_ptr<BufferManager> Sptr;
+    virtual ~BufferManager() {}
     static Sptr make(const std::string &name, const BufferManagerArgs &args)
     {
         auto p = std::make_shared<BufferManager>();
         p->name = name; p->args = args;
         return p;
     }
+    // A custom manager (a block's getInputBufferManager / getOutputBufferManager) owns where the
+    // port's bytes live: the scheduler takes the port's slab from allocate() and gives it back
+    // with release().  The default is the heap.  (Real Pothos: a BufferManager subclass hands out
+    // ManagedBuffers over its own SharedBuffer slabs; same ownership, richer interface.)
+    virtual void *allocate(size_t bytes) { return std::malloc(bytes); }
+    virtual void release(void *p) { std::free(p); }
+    virtual bool custom() const { return false; }
     std::string name;
     BufferManagerArgs args;
 };
@@ -191,8 +200,9 @@ class Block;
 // ---- ports ----------------------------------------------------------------------------------
 class InputPort {
 public:
-    size_t elements() const { return (_q.size() - _head) / _dtype.size(); }
-    BufferChunk buffer() { return BufferChunk::view(_q.data() + _head, _q.size() - _head, _dtype); }
+    ~InputPort() { if (_q) _mgr->release(_q); }
+    size_t elements() const { return (_size - _head) / _dtype.size(); }
+    BufferChunk buffer() { return BufferChunk::view(_q + _head, _size - _head, _dtype); }
     void consume(size_t n) { _consumed += n; }
     bool hasMessage() const { return _mhead < _msgs.size(); }
     Object popMessage()
@@ -206,19 +216,47 @@ public:
     const DType &dtype() const { return _dtype; }
     unsigned long long totalElements() const { return _total; }
 
-    // scheduler side
+    // scheduler side: the port's bytes live in ONE slab from the port's buffer manager (heap by
+    // default, e.g. page-locked memory when the consuming block says so); the unread bytes are
+    // moved to the front when the slab would overflow, the slab grows geometrically
+    void _setManager(const BufferManager::Sptr &m)
+    {
+        if (!m || !m->custom()) return;
+        if (_q) {
+            uint8_t *n = static_cast<uint8_t *>(m->allocate(_cap));
+            if (!n) throw Exception("InputPort", "buffer manager: out of memory");
+            std::memcpy(n, _q + _head, _size - _head);
+            _mgr->release(_q);
+            _q = n; _size -= _head; _head = 0;
+        }
+        _mgr = m;
+    }
     void _pushBytes(const void *p, size_t bytes)
     {
-        const uint8_t *b = static_cast<const uint8_t *>(p);
-        if (_head > (1u << 20) && _head > _q.size() / 2) { _q.erase(_q.begin(), _q.begin() + long(_head)); _head = 0; }
-        _q.insert(_q.end(), b, b + bytes);
+        if (_size + bytes > _cap) {
+            const size_t live = _size - _head;
+            if (_head >= live + bytes && live + bytes <= _cap) {
+                std::memmove(_q, _q + _head, live);            // enough room once the consumed front is dropped
+            } else {
+                size_t ncap = _cap ? _cap : size_t(1) << 16;
+                while (ncap < 2 * (live + bytes)) ncap *= 2;
+                uint8_t *n = static_cast<uint8_t *>(_mgr->allocate(ncap));
+                if (!n) throw Exception("InputPort", "buffer manager: out of memory");
+                if (live) std::memcpy(n, _q + _head, live);
+                if (_q) _mgr->release(_q);
+                _q = n; _cap = ncap;
+            }
+            _size = live; _head = 0;
+        }
+        std::memcpy(_q + _size, p, bytes);
+        _size += bytes;
     }
     void _pushMessage(const Object &o) { _msgs.push_back(o); }
     bool _commit()
     {
         bool did = _consumed > 0 || _progress;
         _head += _consumed * _dtype.size();
-        if (_head > _q.size()) _head = _q.size();
+        if (_head > _size) _head = _size;
         _total += _consumed;
         _consumed = 0; _progress = false;
         if (_mhead > 1024 && _mhead == _msgs.size()) { _msgs.clear(); _mhead = 0; }
@@ -230,7 +268,9 @@ public:
     DType _dtype;
 
 private:
-    std::vector<uint8_t> _q;
+    BufferManager::Sptr _mgr = std::make_shared<BufferManager>();
+    uint8_t *_q = nullptr;
+    size_t _cap = 0, _size = 0;
     size_t _head = 0, _consumed = 0, _reserve = 0, _mhead = 0;
     unsigned long long _total = 0;
     bool _progress = false;
@@ -403,7 +443,7 @@ public:
                 auto mgr = b->getOutputBufferManager(n, "");
                 if (mgr) b->output(n)->_bufferBytes = std::max(b->output(n)->_bufferBytes, mgr->args.bufferSize);
             }
-            for (auto &n : b->inputNames()) (void)b->getInputBufferManager(n, "");
+            for (auto &n : b->inputNames()) b->input(n)->_setManager(b->getInputBufferManager(n, ""));
             b->activate();
         }
         _active = true;

@@ -135,7 +135,17 @@ struct LoopOut
     double seconds;                /* wall time of the feed/run loop (blocks already constructed) */
     unsigned long long n_decoded;  /* decoded packets in total (lengths[] only keeps the first 64) */
     unsigned long long windows;    /* windows submitted to the GPU by our demod (incl. unused speculation) */
+    unsigned long long pinned_inputs; /* work() calls of our demod whose input port buffer was page-locked */
 };
+
+/* Which encoder / modulator / decoder the entry points below instantiate: bit 0 = our LoRaEncoderB200,
+ * bit 1 = our LoRaModB200, bit 2 = our LoRaDecoderB200 (lora-sdr_b200/host/blocks/LoRaCodecB200.cpp,
+ * registered here under *_b200 paths next to the unmodified reference blocks); 0 = all reference. */
+static int g_b200_codec = 0;
+extern "C" void loopback_use_b200_codec(int mask) { g_b200_codec = mask; }
+static const char *encoderPath(void) { return (g_b200_codec & 1) ? "/lora/lora_encoder_b200" : "/lora/lora_encoder"; }
+static const char *modPath(void) { return (g_b200_codec & 2) ? "/lora/lora_mod_b200" : "/lora/lora_mod"; }
+static const char *decoderPath(void) { return (g_b200_codec & 4) ? "/lora/lora_decoder_b200" : "/lora/lora_decoder"; }
 
 /* Transmit side: packets -> encoder -> mod -> (+ noise) -> IQ samples (complex64) into iq_out. */
 int loopback_tx(const LoopCfg *cfg, const unsigned char *payloads, const int *lengths, int n_packets,
@@ -144,8 +154,8 @@ int loopback_tx(const LoopCfg *cfg, const unsigned char *payloads, const int *le
     try
     {
         static const char *crs[] = {"4/4", "4/5", "4/6", "4/7", "4/8"};
-        std::unique_ptr<Pothos::Block> encoder(Pothos::BlockRegistry::make("/lora/lora_encoder"));
-        std::unique_ptr<Pothos::Block> mod(Pothos::BlockRegistry::make("/lora/lora_mod", size_t(cfg->sf)));
+        std::unique_ptr<Pothos::Block> encoder(Pothos::BlockRegistry::make(encoderPath()));
+        std::unique_ptr<Pothos::Block> mod(Pothos::BlockRegistry::make(modPath(), size_t(cfg->sf)));
         NoiseAdder noise(cfg->sigma, cfg->seed);
         encoder->call("setSpreadFactor", size_t(cfg->sf));
         encoder->call("setCodingRate", std::string(crs[cfg->cr]));
@@ -188,7 +198,7 @@ int loopback_encode(const LoopCfg *cfg, const unsigned char *payload, int length
     try
     {
         static const char *crs[] = {"4/4", "4/5", "4/6", "4/7", "4/8"};
-        std::unique_ptr<Pothos::Block> encoder(Pothos::BlockRegistry::make("/lora/lora_encoder"));
+        std::unique_ptr<Pothos::Block> encoder(Pothos::BlockRegistry::make(encoderPath()));
         encoder->call("setSpreadFactor", size_t(cfg->sf));
         encoder->call("setCodingRate", std::string(crs[cfg->cr]));
         ministream::Topology topology;
@@ -223,7 +233,7 @@ int loopback_encode_cfg(const int *cfg6, const unsigned char *payload, int lengt
     try
     {
         static const char *crs[] = {"4/4", "4/5", "4/6", "4/7", "4/8"};
-        std::unique_ptr<Pothos::Block> encoder(Pothos::BlockRegistry::make("/lora/lora_encoder"));
+        std::unique_ptr<Pothos::Block> encoder(Pothos::BlockRegistry::make(encoderPath()));
         encoder->call("setSpreadFactor", size_t(cfg6[0]));
         encoder->call("setSymbolSize", size_t(cfg6[1]));
         encoder->call("setCodingRate", std::string(crs[cfg6[2]]));
@@ -261,7 +271,7 @@ int loopback_mod(const LoopCfg *cfg, const unsigned short *syms, int n_syms,
 {
     try
     {
-        std::unique_ptr<Pothos::Block> mod(Pothos::BlockRegistry::make("/lora/lora_mod", size_t(cfg->sf)));
+        std::unique_ptr<Pothos::Block> mod(Pothos::BlockRegistry::make(modPath(), size_t(cfg->sf)));
         mod->call("setAmplitude", cfg->ampl);
         mod->call("setPadding", size_t(cfg->padding));
         mod->call("setSync", (unsigned char)(cfg->sync));
@@ -298,7 +308,7 @@ int loopback_decode(const int *cfg8, const unsigned short *syms, int n_syms, uns
     try
     {
         static const char *crs[] = {"4/4", "4/5", "4/6", "4/7", "4/8"};
-        std::unique_ptr<Pothos::Block> decoder(Pothos::BlockRegistry::make("/lora/lora_decoder"));
+        std::unique_ptr<Pothos::Block> decoder(Pothos::BlockRegistry::make(decoderPath()));
         decoder->call("setSpreadFactor", size_t(cfg8[0]));
         decoder->call("setSymbolSize", size_t(cfg8[1]));
         decoder->call("setCodingRate", std::string(crs[cfg8[2]]));
@@ -342,7 +352,7 @@ int loopback_rx(const LoopCfg *cfg, const float *iq, unsigned long long n_sample
         static const char *crs[] = {"4/4", "4/5", "4/6", "4/7", "4/8"};
         std::unique_ptr<Pothos::Block> demod(Pothos::BlockRegistry::make(
             cfg->use_b200 ? "/lora/lora_demod_b200" : "/lora/lora_demod_ref0", size_t(cfg->sf)));
-        std::unique_ptr<Pothos::Block> decoder(Pothos::BlockRegistry::make("/lora/lora_decoder"));
+        std::unique_ptr<Pothos::Block> decoder(Pothos::BlockRegistry::make(decoderPath()));
         decoder->call("setSpreadFactor", size_t(cfg->sf));
         decoder->call("setCodingRate", std::string(crs[cfg->cr]));
         demod->call("setSync", (unsigned char)(cfg->sync));
@@ -394,6 +404,7 @@ int loopback_rx(const LoopCfg *cfg, const float *iq, unsigned long long n_sample
         if (cfg->use_b200) out->launches = demod->call<unsigned long long>("getKernelLaunches");
         if (cfg->use_b200) out->calls = demod->call<unsigned long long>("getDemodCalls");
         if (cfg->use_b200) out->windows = demod->call<unsigned long long>("getDemodWindows");
+        if (cfg->use_b200) out->pinned_inputs = demod->call<unsigned long long>("getPinnedInputs");
         out->samples = demod->input("0")->totalElements();
         for (auto &l : demod->output("raw")->collectedLabels)
         {

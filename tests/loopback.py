@@ -21,7 +21,8 @@ class LoopOut(C.Structure):
                 ("n_labels", C.c_int), ("labels", (C.c_char * 24) * 256), ("label_index", C.c_ulonglong * 256),
                 ("n_signals", C.c_int), ("signal_power", C.c_float * 64), ("signal_error", C.c_int * 64),
                 ("error", C.c_char * 256), ("calls", C.c_ulonglong),
-                ("seconds", C.c_double), ("n_decoded", C.c_ulonglong), ("windows", C.c_ulonglong)]
+                ("seconds", C.c_double), ("n_decoded", C.c_ulonglong), ("windows", C.c_ulonglong),
+                ("pinned_inputs", C.c_ulonglong)]
 
 
 def available():
@@ -40,6 +41,14 @@ def _lib():
     L.loopback_mod.argtypes = [C.POINTER(LoopCfg), C.c_void_p, C.c_int, C.c_void_p, C.c_ulonglong,
                                C.POINTER(C.c_ulonglong), C.c_char_p]
     return L
+
+
+def use_b200_codec(mask):
+    """Which encoder (bit 0) / modulator (bit 1) / decoder (bit 2) the helpers below instantiate:
+    our block shells (lora-sdr_b200/host/blocks/LoRaCodecB200.cpp) instead of the reference blocks."""
+    L = _lib()
+    L.loopback_use_b200_codec.argtypes = [C.c_int]
+    L.loopback_use_b200_codec(int(mask))
 
 
 def encode(sf, cr, payload):
@@ -134,6 +143,7 @@ def receive(sf, cr, iq, use_b200=False, debug_ports=True, mtu=512, sync=0x12, th
         o += out.sym_lengths[i]
     labels = [(out.labels[i].value.decode(), int(out.label_index[i])) for i in range(out.n_labels)]
     return dict(decoded=dec, symbols=syms, dropped=int(out.dropped), launches=int(out.launches), calls=int(out.calls), seconds=float(out.seconds), n_decoded=int(out.n_decoded), windows=int(out.windows),
+                pinned_inputs=int(out.pinned_inputs),
                 samples=int(out.samples), labels=labels,
                 power=[float(out.signal_power[i]) for i in range(out.n_signals)],
                 error=[int(out.signal_error[i]) for i in range(out.n_signals)])

@@ -68,3 +68,5 @@ def test_b200_demod_is_a_drop_in(cuda_ok, sf, cr, sigma, debug_ports, feed_windo
     assert got["launches"] > 0
     if feed_windows == 0:
         assert 0 < got["calls"] < got["samples"] // n
+    # the block's input port lives in page-locked memory (its own BufferManager): every call saw it
+    assert got["pinned_inputs"] > 0
