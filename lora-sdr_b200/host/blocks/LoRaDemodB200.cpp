@@ -532,3 +532,175 @@ private:
 
 static Pothos::BlockRegistry registerLoRaDemodB200(
     LORAB200_REGISTRY_PATH, &LoRaDemodB200::make);
+
+/***********************************************************************
+ * |PothosDoc LoRa Demod, many channels (B200)
+ *
+ * K independent LoRa channels of the same spread factor behind ONE block: input ports "0" .. "K-1"
+ * (complex sample streams), output ports "0" .. "K-1" (symbol packets, as the LoRa Demod block posts
+ * them).  One work() call hands every port's buffer to the on-device receiver in ONE launch
+ * (lorab200_rx_host -> one CTA per channel); each channel keeps its own frame-sync state, exactly as K
+ * separate LoRa Demod blocks would (LoRaDemod.cpp:145-327 per channel), without K threads and K launches.
+ * No debug ports.  Signals error / power / snr carry the channel number as a first argument.
+ *
+ * |category /LoRa
+ * |keywords lora
+ *
+ * |param sf[Spread factor] |default 10
+ * |param channels[Channels] Number of input / output port pairs. |default 8
+ * |param sync[Sync word] |default 0x12
+ * |param thresh[Threshold] |units dB |default -30.0
+ * |param mtu[Symbol MTU] |units symbols |default 256
+ *
+ * |factory /lora/lora_demod_multi(sf, channels)
+ * |setter setSync(sync)
+ * |setter setThreshold(thresh)
+ * |setter setMTU(mtu)
+ **********************************************************************/
+class LoRaDemodMultiB200 : public Pothos::Block
+{
+public:
+    LoRaDemodMultiB200(const size_t sf, const size_t channels):
+        N(size_t(1) << sf), K(channels), _ctx(nullptr), _sync(0x12), _thresh(-30.0f), _mtu(256), _maxBatch(4096)
+    {
+        if (K == 0 or K > 4096) throw Pothos::InvalidArgumentException("LoRaDemodMultiB200", "channels must be 1..4096");
+        this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodMultiB200, setSync));
+        this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodMultiB200, setThreshold));
+        this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodMultiB200, setMTU));
+        this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodMultiB200, setMaxBatch));
+        this->registerCall(this, POTHOS_FCN_TUPLE(LoRaDemodMultiB200, getKernelLaunches));
+        for (size_t c = 0; c < K; c++)
+        {
+            this->setupInput(c, typeid(std::complex<float>));
+            this->setupOutput(c);
+            this->input(c)->setReserve(N*2);
+        }
+        this->registerSignal("error");
+        this->registerSignal("power");
+        this->registerSignal("snr");
+        int device = 0;
+        if (const char *env = std::getenv("LORAB200_DEVICE")) device = std::atoi(env);
+        const int st = lorab200_create(&_ctx, device, int(sf), LORAB200_FLAG_DEFAULT);
+        if (st != LORAB200_OK)
+            throw Pothos::Exception("LoRaDemodMultiB200(" + std::to_string(sf) + ")",
+                std::string(lorab200_strerror(st)) + ": " + lorab200_last_error(nullptr));
+        _state.resize(K);
+        _sigEmitted.assign(K, 0);
+    }
+
+    ~LoRaDemodMultiB200(void) { lorab200_destroy(_ctx); }
+
+    static Block *make(const size_t sf, const size_t channels) { return new LoRaDemodMultiB200(sf, channels); }
+
+    void setSync(const unsigned char sync) { _sync = sync; }
+    void setThreshold(const double thresh_dB) { _thresh = thresh_dB; }
+    void setMTU(const size_t mtu) { _mtu = mtu; }
+    void setMaxBatch(const size_t n) { _maxBatch = std::max<size_t>(1, n); }
+    unsigned long long getKernelLaunches(void) const { return lorab200_kernel_launches(_ctx); }
+
+    void activate(void)
+    {
+        std::memset(_state.data(), 0, _state.size()*sizeof(lorab200_rx_state));   //all zero == rx_reset
+        _sigEmitted.assign(K, 0);
+    }
+
+    void work(void)
+    {
+        //one launch over the channels that have at least two symbols buffered (LoRaDemod.cpp:148), for as
+        //many samples as the shortest of them holds; the scheduler calls again while any port has more
+        if (_rxMtu != _mtu)
+        {
+            _partial.assign(K*_mtu, 0);
+            _symbols.assign(K*size_t(kRxMaxPackets)*_mtu, 0);
+            _rxMtu = _mtu;
+        }
+        std::vector<size_t> run;
+        size_t n = _maxBatch*N;
+        for (size_t c = 0; c < K; c++)
+        {
+            const size_t have = this->input(c)->elements();
+            if (have < N*2) continue;
+            run.push_back(c);
+            n = std::min(n, have);
+        }
+        const size_t R = run.size();
+        if (R == 0) return;
+        std::vector<const float *> iq(R);
+        std::vector<lorab200_rx_state> state(R);
+        std::vector<int16_t> partial(R*_mtu);
+        for (size_t i = 0; i < R; i++)
+        {
+            const size_t c = run[i];
+            iq[i] = reinterpret_cast<const float *>(this->input(c)->buffer().as<const std::complex<float> *>());
+            state[i] = _state[c];
+            std::memcpy(partial.data() + i*_mtu, _partial.data() + c*_mtu, _mtu*sizeof(int16_t));
+        }
+        std::vector<lorab200_rx_packet> info(R*size_t(kRxMaxPackets));
+        std::vector<int32_t> npk(R);
+        std::vector<uint64_t> consumed(R);
+        const int rc = lorab200_rx_host(_ctx, iq.data(), R, n, _sync, _thresh, _mtu, state.data(), partial.data(),
+            _symbols.data(), info.data(), npk.data(), consumed.data(), kRxMaxPackets);
+        if (rc != LORAB200_OK)
+            throw Pothos::Exception("LoRaDemodMultiB200::work()", std::string(lorab200_strerror(rc)) + ": " + lorab200_last_error(_ctx));
+        for (size_t i = 0; i < R; i++)
+        {
+            const size_t c = run[i];
+            _state[c] = state[i];
+            std::memcpy(_partial.data() + c*_mtu, partial.data() + i*_mtu, _mtu*sizeof(int16_t));
+            const lorab200_rx_packet *ci = info.data() + i*size_t(kRxMaxPackets);
+            for (int32_t p = 0; p < npk[i]; p++)
+            {
+                if (not (p == 0 and _sigEmitted[c]))
+                {
+                    this->emitSignal("error", int(c), int(ci[p].error));
+                    this->emitSignal("power", int(c), ci[p].power);
+                    this->emitSignal("snr", int(c), ci[p].snr);
+                }
+                _sigEmitted[c] = 0;
+                Pothos::Packet pkt;
+                pkt.payload = Pothos::BufferChunk(typeid(int16_t), _mtu);
+                std::memcpy(pkt.payload.as<int16_t *>(), _symbols.data() + (i*size_t(kRxMaxPackets) + size_t(p))*_mtu,
+                    size_t(ci[p].length)*sizeof(int16_t));
+                pkt.payload.length = size_t(ci[p].length)*sizeof(int16_t);
+                this->output(c)->postMessage(pkt);
+            }
+            const lorab200_rx_state &st = _state[c];
+            if ((st.phase == lorab200::RX_QUARTERCHIRP or st.phase == lorab200::RX_DATASYMBOLS) and not _sigEmitted[c])
+            {
+                this->emitSignal("error", int(c), int(st.sig_error));
+                this->emitSignal("power", int(c), st.sig_power);
+                this->emitSignal("snr", int(c), st.sig_snr);
+                _sigEmitted[c] = 1;
+            }
+            this->input(c)->consume(size_t(consumed[i]));
+        }
+    }
+
+    //! page-locked input slabs, large enough for a batch (as the single-channel block)
+    Pothos::BufferManager::Sptr getInputBufferManager(const std::string &, const std::string &)
+    {
+        auto mgr = std::make_shared<PinnedBufferManager>();
+        mgr->name = "lorab200_pinned";
+        mgr->args.bufferSize = std::max(mgr->args.bufferSize, N*66*sizeof(std::complex<float>));
+        return mgr;
+    }
+
+private:
+    enum { kRxMaxPackets = 16 };
+    const size_t N, K;
+    lorab200_ctx *_ctx;
+    unsigned char _sync;
+    float _thresh;
+    size_t _mtu, _maxBatch;
+    size_t _rxMtu = 0;
+    std::vector<lorab200_rx_state> _state;
+    std::vector<int16_t> _partial, _symbols;
+    std::vector<char> _sigEmitted;
+};
+
+#ifndef LORAB200_MULTI_REGISTRY_PATH
+#define LORAB200_MULTI_REGISTRY_PATH "/lora/lora_demod_multi"
+#endif
+static Pothos::BlockRegistry registerLoRaDemodMultiB200(
+    LORAB200_MULTI_REGISTRY_PATH, &LoRaDemodMultiB200::make);
+

@@ -403,6 +403,13 @@ public:
             return f(a[0].convert<typename std::decay<A0>::type>());
         };
     }
+    template <typename A0, typename A1> BlockRegistry(const std::string &path, Block *(*f)(A0, A1))
+    {
+        table()[path] = [f, path](const std::vector<Object> &a) {
+            if (a.size() != 2) throw InvalidArgumentException("BlockRegistry::make(" + path + ")", "expected 2 arguments");
+            return f(a[0].convert<typename std::decay<A0>::type>(), a[1].convert<typename std::decay<A1>::type>());
+        };
+    }
     template <typename... A> static Block *make(const std::string &path, A &&...a)
     {
         auto it = table().find(path);

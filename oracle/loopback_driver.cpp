@@ -429,4 +429,60 @@ int loopback_rx(const LoopCfg *cfg, const float *iq, unsigned long long n_sample
     }
 }
 
+/* K channels through ONE LoRaDemodMultiB200 block (one launch per work() call): channel c reads
+ * iq + c*n_samples.  Per channel: the symbol packets (at most 16, each at most cfg->mtu symbols), the
+ * error signals in order, the samples consumed. */
+int loopback_rx_multi(const LoopCfg *cfg, const float *iq, int n_channels, unsigned long long n_samples,
+                      unsigned long long feed, int *n_packets, int *lengths, short *symbols, int *errors,
+                      unsigned long long *consumed, unsigned long long *launches, char *err256)
+{
+    try
+    {
+        std::unique_ptr<Pothos::Block> demod(Pothos::BlockRegistry::make("/lora/lora_demod_multi_b200", size_t(cfg->sf), size_t(n_channels)));
+        demod->call("setSync", (unsigned char)(cfg->sync));
+        demod->call("setMTU", size_t(cfg->mtu));
+        demod->call("setThreshold", double(cfg->thresh));
+        ministream::Topology topology;
+        topology.add(demod.get());
+        for (int c = 0; c < n_channels; c++) demod->output(std::to_string(c))->collect = true;
+        topology.commit();
+        const cf *src = reinterpret_cast<const cf *>(iq);
+        if (feed == 0) feed = n_samples;
+        for (unsigned long long at = 0; at < n_samples; at += feed)
+        {
+            const unsigned long long n = std::min(feed, n_samples - at);
+            for (int c = 0; c < n_channels; c++)
+                ministream::Topology::feedStream(demod.get(), std::to_string(c), src + size_t(c) * n_samples + at, n * sizeof(cf));
+            topology.run();
+        }
+        for (int c = 0; c < n_channels; c++)
+        {
+            const auto &msgs = demod->output(std::to_string(c))->collectedMessages;
+            n_packets[c] = int(msgs.size());
+            for (size_t p = 0; p < msgs.size() && p < 16; p++)
+            {
+                const auto &pkt = msgs[p].extract<Pothos::Packet>();
+                const int n = int(pkt.payload.length / 2);
+                lengths[c * 16 + int(p)] = n;
+                std::memcpy(symbols + (size_t(c) * 16 + p) * size_t(cfg->mtu), pkt.payload.as<const void *>(), size_t(n) * 2);
+            }
+            consumed[c] = demod->input(std::to_string(c))->totalElements();
+        }
+        std::vector<int> ne(size_t(n_channels), 0);
+        for (auto &s : demod->signalLog)
+        {
+            if (s.first != "error") continue;
+            const int c = s.second[0].convert<int>();
+            if (ne[size_t(c)] < 16) errors[c * 16 + ne[size_t(c)]++] = s.second[1].convert<int>();
+        }
+        *launches = demod->call<unsigned long long>("getKernelLaunches");
+        return 0;
+    }
+    catch (const std::exception &ex)
+    {
+        std::strncpy(err256, ex.what(), 255);
+        return -1;
+    }
+}
+
 } /* extern "C" */

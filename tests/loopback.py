@@ -149,6 +149,32 @@ def receive(sf, cr, iq, use_b200=False, debug_ports=True, mtu=512, sync=0x12, th
                 error=[int(out.signal_error[i]) for i in range(out.n_signals)])
 
 
+def receive_multi(sf, streams, mtu=512, sync=0x12, thresh=-30.0, feed=0):
+    """K equally long IQ streams through ONE LoRaDemodMultiB200 block.  Returns, per channel, the symbol
+    packets, the error signals and the samples consumed, plus the kernel launches of the block."""
+    L = _lib()
+    L.loopback_rx_multi.argtypes = [C.POINTER(LoopCfg), C.c_void_p, C.c_int, C.c_ulonglong, C.c_ulonglong] + [C.c_void_p] * 5 + \
+        [C.POINTER(C.c_ulonglong), C.c_char_p]
+    buf = np.ascontiguousarray(streams, np.complex64)
+    k, n = buf.shape
+    cfg = LoopCfg(sf, 0, 1, 0, 0, mtu, sync, 1.0, 0.0, thresh, 0)
+    npk = np.zeros(k, np.int32)
+    lens = np.zeros((k, 16), np.int32)
+    syms = np.zeros((k, 16, mtu), np.int16)
+    errs = np.zeros((k, 16), np.int32)
+    cons = np.zeros(k, np.uint64)
+    launches = C.c_ulonglong()
+    err = C.create_string_buffer(256)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    if L.loopback_rx_multi(C.byref(cfg), vp(buf), k, n, feed, vp(npk), vp(lens), vp(syms), vp(errs), vp(cons), C.byref(launches), err):
+        raise RuntimeError(err.value.decode())
+    out = []
+    for c in range(k):
+        out.append(dict(symbols=[syms[c, p, : lens[c, p]].copy() for p in range(min(int(npk[c]), 16))],
+                        error=[int(errs[c, p]) for p in range(min(int(npk[c]), 16))], samples=int(cons[c])))
+    return out, int(launches.value)
+
+
 def run(sf, cr, packets, use_b200=False, debug_ports=True, padding=512, mtu=512, sync=0x12, ampl=1.0,
         sigma=0.0, thresh=-30.0, seed=1, feed=0):
     iq = transmit(sf, cr, packets, padding=padding, sync=sync, ampl=ampl, sigma=sigma, seed=seed)

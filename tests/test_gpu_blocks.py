@@ -119,3 +119,37 @@ def test_all_four_blocks_are_ours(cuda_ok, sf, cr, sigma):
     assert got["decoded"] == pk
     assert got["dropped"] == ref["dropped"] == 0
     assert got["launches"] > 0 and got["pinned_inputs"] > 0
+
+
+@pytest.mark.parametrize("sf,thresh,feed_windows", [(7, -30.0, 0), (8, -4.0, 29), (10, -30.0, 0)])
+def test_many_channels_behind_one_block(cuda_ok, sf, thresh, feed_windows):
+    """LoRaDemodMultiB200: K input ports, K output ports, one launch per work() call; every channel's
+    packets, error signals and consumed samples equal those of a separate reference LoRaDemod block fed
+    the same stream."""
+    rng = np.random.default_rng(70 + sf)
+    k, mtu = 6, 96
+    streams = []
+    for c in range(k):
+        pk = [bytes(rng.integers(0, 256, int(rng.integers(4, 30)), dtype=np.uint8)) for _ in range(2)]
+        iq = loopback.transmit(sf, 4, pk, padding=70, sigma=0.05, seed=500 * sf + c)
+        lead = int(rng.integers(0, 3 << sf))
+        noise = (rng.standard_normal(lead) + 1j * rng.standard_normal(lead)).astype(np.complex64) * np.float32(0.05)
+        streams.append(np.concatenate([noise, iq]))
+    n = max(s.size for s in streams)
+    buf = np.zeros((k, n), np.complex64)
+    for c, s in enumerate(streams):
+        buf[c, : s.size] = s
+    feed = feed_windows * (1 << sf) + (3 if feed_windows else 0)
+    got, launches = loopback.receive_multi(sf, buf, mtu=mtu, thresh=thresh, feed=feed)
+    total = 0
+    for c in range(k):
+        ref = loopback.receive(sf, 4, buf[c], use_b200=False, debug_ports=True, mtu=mtu, thresh=thresh, feed=feed)
+        assert len(got[c]["symbols"]) == len(ref["symbols"]), f"channel {c}"
+        for a, b in zip(got[c]["symbols"], ref["symbols"]):
+            assert np.array_equal(a, b)
+        assert got[c]["error"] == ref["error"]
+        assert got[c]["samples"] == ref["samples"]
+        total += len(ref["symbols"])
+    assert total >= k
+    if feed_windows == 0:
+        assert launches <= 4              # the whole buffer of every channel in a handful of launches

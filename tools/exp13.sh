@@ -1,2 +1,2 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_blocks.py tests/test_loopback.py -x -q -m gpu 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_gpu_blocks.py -x -q -m gpu 2>&1 | tail -15
