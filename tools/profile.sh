@@ -1,14 +1,17 @@
 #!/bin/bash
 # Run ON THE GPU BOX (through gpurun): ncu captures the judge wants, into gpurun_out/.
 #   1. launch list of the default bench command (every launch with its device time)
-#   2. one --set full capture of the fused kernel for SF 7 / 10 / 12
+#   2. one --set full capture of the fused kernel for SF 7 / 10 / 12 (+ the walking fine-tune form)
 set -u
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_sf7.csv \
-    python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/launches_sf7.log 2>&1
+    python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-sweep > gpurun_out/launches_sf7.log 2>&1
+L=lora-sdr_b200/liblorab200.so
 for sf in 7 10 12; do
   w=$([ $sf = 7 ] && echo 65536 || echo 16384)
-  ncu --set full --clock-control none --import-source on -k regex:demod_fused -s 8 -c 1 -f -o gpurun_out/prof_sf$sf \
-      python bench.py --sf $sf --windows $w --steps 12 --warmup 4 --no-cpu-baseline > gpurun_out/ncu_sf$sf.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:demod_fused -s 4 -c 1 -f -o gpurun_out/prof_sf$sf \
+      tools/kbench --lib $L --sf $sf --windows $w --steps 4 --reps 1 > gpurun_out/ncu_sf$sf.log 2>&1
   tail -1 gpurun_out/ncu_sf$sf.log | cut -c1-80
 done
+ncu --set full --clock-control none --import-source on -k regex:demod_fused -s 4 -c 1 -f -o gpurun_out/prof_walk_sf7 \
+    tools/kbench --lib $L --sf 7 --windows 65536 --steps 4 --reps 1 --fine-step 1.28 > gpurun_out/ncu_walk.log 2>&1

@@ -26,3 +26,22 @@ for sf in range(7, 13):
         assert d.last_kernel.startswith("fused"), (sf, kw, d.last_kernel)
     d.close()
     print("sf", sf, "ok", flush=True)
+
+# the receiver kernels (speculative batches and the one-window cross-check) on a few short streams:
+# frames from the device encoder + modulator, a little noise, odd lead-ins
+for sf in (7, 9, 10, 12):
+    for flags in (0, 1):
+        d = m.Demod(sf, flags=flags)
+        payloads = torch.from_numpy(rng.integers(0, 256, (3, 9), dtype=np.uint8)).cuda()
+        syms, nsy = d.encode_dev(payloads, rdd=4, crc=True)
+        iq = d.mod_dev(syms, padding=40, ampl=1.0, mode=m.MOD_IDEAL)
+        g = torch.Generator("cuda").manual_seed(sf)
+        iq = iq + 0.05 * torch.view_as_complex(torch.randn((*iq.shape, 2), device=iq.device, generator=g))
+        lead = 0.05 * torch.view_as_complex(torch.randn((3, (5 << sf) // 4 + 1, 2), device=iq.device, generator=g))
+        stream = torch.cat([lead, iq], dim=1).contiguous()
+        for thresh in (-30.0, -5.0):
+            r = d.rx_dev(stream, thresh=thresh, mtu=48, max_packets=4)
+            torch.cuda.synchronize()
+            assert int(r["n_packets"].min()) >= 1, (sf, flags, thresh)
+        d.close()
+    print("rx sf", sf, "ok", flush=True)
