@@ -157,7 +157,7 @@ __device__ __forceinline__ float cx_abs(float2 a)
 // contract is 1e-4 dB (tests/test_gpu_parity.py POWER_TOL_DB).  lorab200_demod_host finalises
 // on the host with the host libm instead and is bit-exact.
 __device__ __forceinline__ void finalize_device(const RawResult &r, float power_scale,
-                                                lorab200_result *out)
+                                                lorab200_result *out, bool want_f_index = true)
 {
     const float fundamental = __fsqrt_rn(r.max_mag2);
     lorab200_result o;
@@ -165,6 +165,9 @@ __device__ __forceinline__ void finalize_device(const RawResult &r, float power_
     const float kDbPerLog2 = 3.0102999566f; // 10*log10(2)
     o.power_avg = __fsub_rn(__fmul_rn(kDbPerLog2, __log2f(__double2float_rn(__dsub_rn(r.total, double(r.max_mag2))))), power_scale);
     o.power = __fsub_rn(__fmul_rn(kDbPerLog2, __log2f(r.max_mag2)), power_scale);
+    // (the receiver kernels skip the fractional index -- two double square roots and a double division --
+    //  for windows whose fIndex nothing reads: every state but FRAMESYNC, LoRaDemod.cpp:220)
+    if (!want_f_index) { o.f_index = 0.0f; *out = o; return; }
     const float left = cx_abs(r.left), right = cx_abs(r.right);
     const double demon = __dsub_rn(__dsub_rn(__dmul_rn(2.0, double(fundamental)), double(right)), double(left));
     if (demon == 0.0) o.f_index = 0.0f;

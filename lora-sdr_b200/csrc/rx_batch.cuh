@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
     __shared__ RawResult rawres[K::BR];
     __shared__ RxRoundRes res[K::BR];
     __shared__ unsigned long long off;
-    __shared__ int s_go, s_nwin, s_table, s_x0, s_walk, npk, s_lin_ok, s_lin_step, s_lin_lo, s_force2;
+    __shared__ int s_go, s_nwin, s_table, s_x0, s_walk, npk, s_lin_ok, s_lin_step, s_lin_lo, s_force2, s_solo, s_need_f;
     __shared__ float s_d, s_fw_d;
     __shared__ float2 s_phasor;
 
@@ -116,8 +116,13 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                 int nwin = int(n_avail > (unsigned long long)cap ? cap : n_avail);
                 // phases in which a result moves the next window: the window itself + its look-ahead
                 const bool idle = st.phase == RX_FRAMESYNC && st.ffe == 0.0f && st.fine_index == 0;
-                if (st.phase != RX_DATASYMBOLS && !idle && nwin > 2) nwin = 2;
+                const bool sequential = st.phase != RX_DATASYMBOLS && !idle;
+                if (sequential && nwin > 2) nwin = 2;
                 s_nwin = nwin;
+                // one-window-at-a-time phases of a window that fits one warp: warp 0 runs them alone, without
+                // CTA barriers (the other warps wait at the top of the loop)
+                s_solo = (GROUP == 32 && WPT >= 2 && sequential) ? 1 : 0;
+                s_need_f = (st.phase == RX_FRAMESYNC) ? 1 : 0;   // fIndex only feeds _finefreqError in FRAMESYNC (:220)
                 s_table = st.table;
                 s_x0 = st.fine_index;
                 const float d = __fmul_rn(st.ffe, 128.0f);                // _finefreqError * _fineSteps
@@ -134,10 +139,7 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                 if (!s_walk) s_phasor = p.fine[s_x0];
             }
         };
-        if (tid == 0) plan();
-        for (;;) {
-            __syncthreads();
-            if (!s_go) break;
+        auto compute = [&]() {
             const int nwin = s_nwin;
             const bool walking = s_walk != 0;
             const float2 *chirp = s_table == LORAB200_TABLE_DOWN ? p.down : p.up;
@@ -191,6 +193,10 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                     group_sync<GROUP>(grp);   // the index area is the exchange buffer: gathers done before the scatter
                 }
 
+                // the next step starts somewhere in (off, off + 2N]: whatever it is, it needs samples up to 3N
+                // ahead; pull the part this round does not read into L1 while it computes
+                if (s_solo && k == 0 && t * 16 < N)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(win + 2 * N + t * 16));
                 // ---- load (global, 8-byte aligned), dechirp, fine-tune multiply (LoRaDemod.cpp:157-159) ----
                 c64 r[16];
 #pragma unroll
@@ -313,18 +319,17 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                 group_sync<GROUP>(grp);   // the record is complete; the exchange buffer is free again
                 if (live && t == 0) {
                     RxRoundRes o;
-                    finalize_device(rawres[k], p.power_scale, &o.r);
+                    finalize_device(rawres[k], p.power_scale, &o.r, s_need_f != 0);
                     o.idx_after = walking ? fine_advance_dev(fw, s_x0, (unsigned long long)(k + 1) * N) : s_x0;
                     o.max_mag2 = rawres[k].max_mag2;
                     o.total = rawres[k].total;
                     res[k] = o;
                 }
             }
-            __syncthreads();
-
-            // ---- walk the results through the state machine while the speculation holds -----------------
-            if (tid == 0) {
-                const int have = nwin;                        // windows demodulated in this round
+        };
+        // thread 0 walks the round's results through the state machine while the speculation holds
+        auto walk = [&]() {
+                const int have = s_nwin;                        // windows demodulated in this round
                 const unsigned long long n_avail = (p.n_samples - off) / N;
                 int k = 0;
                 s_force2 = 0;
@@ -350,8 +355,10 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                     }
                     off += a.consume;
                     // is the next demodulated window the one the stream continues with?
+                    // (... and, if the round skipped the fractional index, not a window that needs it)
                     const bool same = a.consume == uint32_t(N) && st.table == s_table &&
-                                      __fmul_rn(st.ffe, 128.0f) == s_d && st.fine_index == res[k].idx_after;
+                                      __fmul_rn(st.ffe, 128.0f) == s_d && st.fine_index == res[k].idx_after &&
+                                      (s_need_f != 0 || st.phase != RX_FRAMESYNC);
                     if (!same) { k = have; break; }
                     ++k;
                 }
@@ -359,8 +366,25 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                     // no progress is only legal when the look-ahead was missing (s_force2); guard against a stall
                     s_force2 = 1;
                 }
-                plan();   // the next round, before the barrier at the top of the loop
+        };
+        if (tid == 0) plan();
+        for (;;) {
+            __syncthreads();
+            if (!s_go) break;
+            if (s_solo) {
+                if (warp_u == 0) {
+                    do {
+                        compute();
+                        __syncwarp();
+                        if (lane == 0) { walk(); plan(); }
+                        __syncwarp();
+                    } while (s_go && s_solo);
+                }
+                continue;
             }
+            compute();
+            __syncthreads();
+            if (tid == 0) { walk(); plan(); }
         }
         if (st.phase == RX_DATASYMBOLS && unsigned(npk) < p.max_packets)
             for (int k = tid; k < st.sym_count; k += K::CTA)

@@ -251,6 +251,18 @@ public:
         std::memcpy(_q + _size, p, bytes);
         _size += bytes;
     }
+    // a framework sizes its port slabs when the topology is committed, not in the data path: harnesses
+    // that push a whole stream at once reserve its size first (page-locked slabs are slow to allocate)
+    void _reserveBytes(size_t cap)
+    {
+        if (cap <= _cap) return;
+        uint8_t *n = static_cast<uint8_t *>(_mgr->allocate(cap));
+        if (!n) throw Exception("InputPort", "buffer manager: out of memory");
+        const size_t live = _size - _head;
+        if (live) std::memcpy(n, _q + _head, live);
+        if (_q) _mgr->release(_q);
+        _q = n; _cap = cap; _size = live; _head = 0;
+    }
     void _pushMessage(const Object &o) { _msgs.push_back(o); }
     bool _commit()
     {

