@@ -191,6 +191,29 @@ __host__ __device__ constexpr int slot_to_x(int c)
     return B0 <= 2 ? c : (B0 == 3 ? (((c & 3) << 1) | (c >> 2)) : (((c & 3) << 2) | (c >> 2)));
 }
 
+// pass-0 scatter offset (elements) of sub-FFT e relative to sub-FFT 0 of the same thread
+template <int SF>
+__host__ __device__ constexpr int sc0_eoff(int e)
+{
+    using C = FusedCfg<SF>;
+    return C::E == 1 ? 0 : C::pad(digit_rev4((e >> 1) * 2 * C::G + (e & 1), SF - C::B0) << C::B0);
+}
+template <int SF>
+__host__ __device__ constexpr bool sc0_split_ok()
+{
+    using C = FusedCfg<SF>;
+    if constexpr (C::E > 1)
+    for (int t = 0; t < C::G; ++t)
+        for (int e = 0; e < C::E; ++e)
+            for (int c = 0; c < C::R0; ++c) {
+                const int il = (e >> 1) * 2 * C::G + 2 * t + (e & 1);
+                const int full = C::pad((digit_rev4(il, SF - C::B0) << C::B0) | slot_to_x<C::B0>(c));
+                const int split = C::pad(digit_rev4(2 * t, SF - C::B0) << C::B0) + sc0_eoff<SF>(e) + C::pad(slot_to_x<C::B0>(c));
+                if (full != split) return false;
+            }
+    return true;
+}
+
 // Two radix-4 stages on 16 register values r[y], y = (qd << 2) | qc, with the
 // per-thread twiddles twa[qc-1] (first stage, same for the 4 butterflies) and
 // twb[qc][qd-1] (second stage).  kissfft.hh:137-157.  Per 16 points: 48 FMUL2 +
@@ -406,13 +429,11 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
     const uint32_t in_off = (uint32_t(wsub) * N + uint32_t(E == 1 ? t : 2 * t)) * 8u;
     const uint32_t chirp_off = uint32_t(E == 1 ? t : 2 * t) * 8u;
     const uint32_t wx = xbase + uint32_t(wsub) * C::WSTRIDE * 8u; // this window's exchange area
-    // pass-0 scatter: j = x(c) | digit_rev(ilow(e)) << B0
-    uint32_t sc0[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int il = (E == 1) ? t : ((e >> 1) * 2 * G + 2 * t + (e & 1));
-        sc0[e] = wx + uint32_t(C::pad(digit_rev4(il, SF - B0) << B0)) * 8u;
-    }
+    // pass-0 scatter: j = x(c) | digit_rev(ilow(e)) << B0.  The e part of ilow lands in bits of j that the
+    // t part never touches and that do not carry through the padding (sc0_split_ok checks every t), so
+    // sub-FFT e scatters to "sub-FFT 0's address + a compile-time constant": one address register, not E
+    static_assert(sc0_split_ok<SF>(), "pass-0 scatter: e offsets are not thread independent");
+    const uint32_t sc0 = wx + uint32_t(C::pad(digit_rev4(E == 1 ? t : 2 * t, SF - B0) << B0)) * 8u;
     // pass-1 gather/scatter: j = lo | y << B0 | hi << (B0+4);  pass-2 gather: j = t | y << (B0+4)
     const uint32_t ga1 = wx + uint32_t(C::pad(lo1 | (hi1 << (B0 + 4)))) * 8u;
     const uint32_t ga2 = wx + uint32_t(C::pad(tL)) * 8u;
@@ -647,7 +668,7 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             for (int e = 0; e < E; ++e)
 #pragma unroll
                 for (int c = 0; c < R0; ++c)
-                    sts64(sc0[e] + uint32_t(C::pad(slot_to_x<B0>(c))) * 8u, r[e * R0 + c]);
+                    sts64(sc0 + uint32_t(sc0_eoff<SF>(e) + C::pad(slot_to_x<B0>(c))) * 8u, r[e * R0 + c]);
             group_sync<GROUP>(grp);
             if constexpr (LATE_REFILL) {
                 if (tg == 0 && k + STAGES < my_tiles) { fence_proxy_async(); issue(k + STAGES, s); }

@@ -121,6 +121,65 @@ __device__ __forceinline__ int fine_advance_dev(const FineWalkDev &fw, int x, un
     return x;
 }
 
+// The same region walk in 32-bit arithmetic (64-bit division is a ~500-cycle software routine on the
+// device; a receiver CTA walks the index a few windows at a time, on its critical path).  Valid when
+// |D|, len and n are below 2^28 (fine_walk32_ok); non-integer steps only -- the integer case and anything
+// out of range take fine_advance_dev.  Same decisions as fine_advance_dev, so the same exact result.
+struct FineWalk32 {
+    int len;
+    float d;
+    int D, Kp;      // Kp == 0x7fffffff: none
+    int ok;
+};
+__device__ __forceinline__ FineWalk32 fine_walk32_make(const FineWalkDev &fw)
+{
+    FineWalk32 w;
+    w.len = fw.len; w.d = fw.d;
+    const long long lim = 1ll << 28;
+    const bool kp_none = fw.Kp == 0x7fffffffffffffffll;
+    w.ok = (!fw.integer && fw.D > -lim && fw.D < lim && fw.len < int(lim) && (kp_none || fw.Kp < lim)) ? 1 : 0;
+    w.D = int(fw.D);
+    w.Kp = kp_none ? 0x7fffffff : int(fw.Kp);
+    return w;
+}
+__device__ __forceinline__ int fine_advance32(const FineWalk32 &fw, int x, unsigned n)
+{
+    const int L = fw.len;
+    while (n > 0) {
+        const int k = x - fw.D;
+        unsigned j = 0;
+        int s = 0;
+        if (k >= 1) {
+            const bool r = (k >= fw.Kp);
+            s = fw.D + 1 - (r ? 1 : 0);
+            if (s == 0) return x;
+            if (s > 0) {
+                const int lb = r ? fw.Kp : 1;
+                j = unsigned(k - lb) / unsigned(s) + 1u;
+            } else {
+                const unsigned a = unsigned(-s);
+                unsigned room = unsigned(L - 1 - x) / a;
+                if (!r && fw.Kp != 0x7fffffff) {
+                    const unsigned q = unsigned(fw.Kp - 1 - k) / a + 1u;
+                    if (q < room) room = q;
+                }
+                j = room;
+            }
+        }
+        if (j == 0) {
+            const int y = fine_next(x, fw.d, L);
+            if (y == x) return x;
+            x = y;
+            --n;
+            continue;
+        }
+        if (j > n) j = n;
+        x = x - int(j) * s;
+        n -= j;
+    }
+    return x;
+}
+
 __global__ void fine_small_kernel(int32_t *__restrict__ X, const FineWalkDev fw, int x0, unsigned long long q_end)
 {
     const unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;

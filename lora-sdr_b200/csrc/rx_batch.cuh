@@ -25,6 +25,15 @@
 
 namespace lorab200 {
 
+// -DLORAB200_RX_PROF: cycle accounting of the one-warp (solo) rounds, printed by the kernel (a tuning aid,
+// not part of the product build)
+#ifdef LORAB200_RX_PROF
+#define RXPROF(i) do { if (s_solo && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); \
+                       prof_acc[i] += t_ - prof_last; prof_last = t_; } } while (0)
+#else
+#define RXPROF(i) do { } while (0)
+#endif
+
 template <int SF>
 struct RxBatchCfg {
     using C = FusedCfg<SF>;
@@ -57,12 +66,18 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ RxState st;
     __shared__ FineWalkDev fw;
+    __shared__ FineWalk32 fw32;
+    __shared__ int s_after[K::BR];           // _fineTuneIndex after each window of the round (its last chunk's walk)
     __shared__ RawResult rawres[K::BR];
     __shared__ RxRoundRes res[K::BR];
     __shared__ unsigned long long off;
     __shared__ int s_go, s_nwin, s_table, s_x0, s_walk, npk, s_lin_ok, s_lin_step, s_lin_lo, s_force2, s_solo, s_need_f;
     __shared__ float s_d, s_fw_d;
     __shared__ float2 s_phasor;
+#ifdef LORAB200_RX_PROF
+    __shared__ long long prof_acc[12], prof_last, prof_rounds;
+    if (threadIdx.x == 0) { for (int i = 0; i < 12; ++i) prof_acc[i] = 0; prof_rounds = 0; asm volatile("mov.u64 %0, %%clock64;" : "=l"(prof_last) :: "memory"); }
+#endif
 
     const int tid = threadIdx.x;
     const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -104,6 +119,10 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
             for (int k = tid; k < st.sym_count; k += K::CTA) slots[k] = p.partial[size_t(ch) * p.cfg.mtu + k];
         __syncthreads();
 
+        // g^n(x) of the fine-tune recurrence: 32-bit region walk when the step allows it
+        auto adv = [&](int x, unsigned long long n) -> int {
+            return (fw32.ok && n < (1ull << 28)) ? fine_advance32(fw32, x, unsigned(n)) : fine_advance_dev(fw, x, n);
+        };
         // thread 0 plans a round: how many windows, under which state (shared s_* variables)
         auto plan = [&]() {
             const unsigned long long left = p.n_samples - off;
@@ -135,6 +154,7 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                     s_lin_ok = (fw.integer || kp_none) ? 1 : 0;
                     s_lin_step = int(fw.integer ? fw.D : fw.D + 1);
                     s_lin_lo = fw.integer ? 0 : int(fw.D + 1 > 0 ? fw.D + 1 : 0);
+                    fw32 = fine_walk32_make(fw);
                 }
                 if (!s_walk) s_phasor = p.fine[s_x0];
             }
@@ -153,10 +173,11 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                 const bool live = k < nwin;
                 const float2 *win = in + off + (unsigned long long)k * N;
 
+                RXPROF(0);   // (top of a pass: plan -> here)
                 // ---- fine-tune indices of this thread's 16 pass-0 samples -----------------------------
                 int fidx[16];
                 if (walking) {
-                    int x = live ? fine_advance_dev(fw, s_x0, (unsigned long long)k * N + 16ull * t) : 0;
+                    int x = live ? adv(s_x0, (unsigned long long)k * N + 16ull * t) : 0;
                     const uint32_t fx = xbase + uint32_t(wsub) * C::FINE_WSTRIDE * 4u;
                     const uint32_t cbase = fx + uint32_t(fine_pad_dyn(16 * t)) * 4u;
                     const int xe = x - 15 * s_lin_step;
@@ -173,6 +194,17 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                         }
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + q * 16u),
                                      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+                    }
+                    // the thread that walked the window's last chunk is one step from the index after the
+                    // window (what the state machine carries on, LoRaDemod.cpp:160-162 after N samples)
+                    if (live && t == G - 1) {
+                        if (linear) {
+                            // all 16 states of the chunk are inside the constant-step region: the 16th step is
+                            // "minus step" too, then the reference's wrap
+                            x = x - 16 * s_lin_step;
+                            if (x < 0) x += p.fine_len; else if (x >= p.fine_len) x -= p.fine_len;
+                        }
+                        s_after[k] = x;
                     }
                     group_sync<GROUP>(grp);
                     const uint32_t gb = fx + uint32_t(fine_pad_dyn(E == 1 ? t : 2 * t)) * 4u;
@@ -193,6 +225,7 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                     group_sync<GROUP>(grp);   // the index area is the exchange buffer: gathers done before the scatter
                 }
 
+                RXPROF(1);   // walking index
                 // the next step starts somewhere in (off, off + 2N]: whatever it is, it needs samples up to 3N
                 // ahead; pull the part this round does not read into L1 while it computes
                 if (s_solo && k == 0 && t * 16 < N)
@@ -211,6 +244,10 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                         r[e * R0 + c] = d;
                     }
 
+#ifdef LORAB200_RX_PROF
+                { const float2 f0 = cunpack(r[0]), f1 = cunpack(r[15]); if (f0.x == 1.2345e30f && f1.y == 3.3e30f) s_go = 0; }  // wait for the loads
+#endif
+                RXPROF(2);   // loads + dechirp
                 // ---- pass 0 butterflies (demod_fused.cuh) ---------------------------------------------
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
@@ -259,6 +296,7 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                     radix16(r, tw2a, tw2b);
                 }
 
+                RXPROF(3);   // FFT
                 // ---- peak scan over this thread's bins tL + G*y (LoRaDetector.hpp:36-48) ----------------
                 float m2[16];
 #pragma unroll
@@ -317,14 +355,16 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                     if (t == 0) { slot->index = bi; slot->max_mag2 = bv; slot->total = sum; }
                 }
                 group_sync<GROUP>(grp);   // the record is complete; the exchange buffer is free again
+                RXPROF(4);   // peak scan, reductions, neighbours
                 if (live && t == 0) {
                     RxRoundRes o;
                     finalize_device(rawres[k], p.power_scale, &o.r, s_need_f != 0);
-                    o.idx_after = walking ? fine_advance_dev(fw, s_x0, (unsigned long long)(k + 1) * N) : s_x0;
+                    o.idx_after = walking ? s_after[k] : s_x0;
                     o.max_mag2 = rawres[k].max_mag2;
                     o.total = rawres[k].total;
                     res[k] = o;
                 }
+                RXPROF(5);   // finalize
             }
         };
         // thread 0 walks the round's results through the state machine while the speculation holds
@@ -376,7 +416,10 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                     do {
                         compute();
                         __syncwarp();
-                        if (lane == 0) { walk(); plan(); }
+                        if (lane == 0) { walk(); RXPROF(6); plan(); RXPROF(7); }
+#ifdef LORAB200_RX_PROF
+                        if (lane == 0) prof_rounds++;
+#endif
                         __syncwarp();
                     } while (s_go && s_solo);
                 }
@@ -394,6 +437,11 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
         if (tid == 0) { p.state[ch] = st; p.n_packets[ch] = npk; p.consumed[ch] = off; }
         __syncthreads();
     }
+#ifdef LORAB200_RX_PROF
+    if (threadIdx.x == 0 && prof_rounds > 0)
+        printf("RXPROF sf=%d rounds=%lld top=%lld walkidx=%lld load=%lld fft=%lld reduce=%lld finalize=%lld walk=%lld plan=%lld\n", SF,
+               prof_rounds, prof_acc[0], prof_acc[1], prof_acc[2], prof_acc[3], prof_acc[4], prof_acc[5], prof_acc[6], prof_acc[7]);
+#endif
 }
 
 } // namespace lorab200
