@@ -495,15 +495,29 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
                 else orbit_r += WPT * N;
                 (void)orbit_state(orb.o, orbit_j, orbit_r);
                 const int seg_y = orb.o.seg[orbit_j].y, seg_c = orb.o.seg[orbit_j].c, os = orb.o.s;
+                if (orbit_r + (N - 1) <= seg_c) {
+                    // the whole window lies inside one progression (decided once per window, the same for
+                    // all its threads): index = base - sample * s, one multiply-add per sample and no
+                    // per-sample test
+                    const int base = seg_y - orbit_r * os;
 #pragma unroll
-                for (int e = 0; e < E; ++e)
+                    for (int e = 0; e < E; ++e)
 #pragma unroll
-                    for (int c = 0; c < R0; ++c) {
-                        const int il = (E == 1) ? t : ((e >> 1) * 2 * G + 2 * t + (e & 1));
-                        int rr = orbit_r + il + (N / R0) * c;
-                        if (rr <= seg_c) fidx[e * R0 + c] = seg_y - rr * os;
-                        else { int jj = orbit_j; fidx[e * R0 + c] = orbit_state(orb.o, jj, rr); }
-                    }
+                        for (int c = 0; c < R0; ++c) {
+                            const int il = (E == 1) ? t : ((e >> 1) * 2 * G + 2 * t + (e & 1));
+                            fidx[e * R0 + c] = base - (il + (N / R0) * c) * os;
+                        }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+#pragma unroll
+                        for (int c = 0; c < R0; ++c) {
+                            const int il = (E == 1) ? t : ((e >> 1) * 2 * G + 2 * t + (e & 1));
+                            int rr = orbit_r + il + (N / R0) * c;
+                            if (rr <= seg_c) fidx[e * R0 + c] = seg_y - rr * os;
+                            else { int jj = orbit_j; fidx[e * R0 + c] = orbit_state(orb.o, jj, rr); }
+                        }
+                }
                 // the phasors do not depend on the IQ tile: gather them (L2) before waiting for it
 #pragma unroll
                 for (int i = 0; i < 16; ++i) fph[i] = __ldg(p.fine + fidx[i]);

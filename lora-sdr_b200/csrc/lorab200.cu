@@ -11,6 +11,9 @@
 #include <cmath>
 #include <limits>
 #include <cstring>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <new>
 #include <atomic>
 #include <chrono>
@@ -133,8 +136,8 @@ private:
 } // namespace
 
 constexpr unsigned long long kFineSmallEntries = 8192; // fine prefix: closed form per entry up to here
-constexpr size_t kRingSlots = 16, kRingSlotBytes = size_t(1) << 20; // pageable-input staging ring (16 MiB pinned)
-constexpr size_t kRingFillThreads = 8;                                // slots filled concurrently (helper threads)
+constexpr size_t kRingSlots = 32, kRingSlotBytes = size_t(1) << 20; // pageable-input staging ring (32 MiB pinned)
+constexpr size_t kRingFillThreads = 16;                                // slots filled concurrently (helper threads)
 constexpr size_t kSmallBatchWindows = 16;          // lorab200_demod_host: zero-copy path up to here
 constexpr size_t kSmallBatchBytes = size_t(256) << 10;
 
@@ -236,6 +239,37 @@ size_t host_threads()
     return h ? h : 1;
 }
 
+// Slot fill: the destination (a pinned slot) is read next by the PCIe DMA engine, not by a CPU, so the
+// copy writes it with non-temporal stores -- no read-for-ownership of the destination lines and no
+// cache pollution (one thread: 16.5 vs 12.6 GB/s for memcpy on the build host).  Falls back to memcpy
+// where AVX2 is absent or the slot is not 32-byte aligned.
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2"))) void stream_copy_avx2(char *d, const char *s, size_t n)
+{
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + i + 64));
+        const __m256i e = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(d + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(d + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(d + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(d + i + 96), e);
+    }
+    if (i < n) std::memcpy(d + i, s + i, n - i);
+    _mm_sfence();
+}
+#endif
+void slot_fill(char *d, const char *s, size_t n)
+{
+#if defined(__x86_64__) && defined(__GNUC__)
+    static const bool avx2 = __builtin_cpu_supports("avx2") && std::getenv("LORAB200_NO_STREAM_COPY") == nullptr;
+    if (avx2 && (reinterpret_cast<uintptr_t>(d) & 31u) == 0) { stream_copy_avx2(d, s, n); return; }
+#endif
+    std::memcpy(d, s, n);
+}
+
 bool is_pageable(const void *p)
 {
     cudaPointerAttributes a;
@@ -261,6 +295,8 @@ int h2d_copy(lorab200_ctx *c, void *dst, const void *src, size_t bytes, cudaStre
     // moves ~12 GB/s (measured, round 1), PCIe gen5 takes ~50: a handful of threads keep it busy.
     size_t par = host_threads() / 2;
     if (par > kRingFillThreads) par = kRingFillThreads;
+    static const long env_par = std::getenv("LORAB200_STAGE_THREADS") ? std::atol(std::getenv("LORAB200_STAGE_THREADS")) : 0;
+    if (env_par > 0 && size_t(env_par) < par) par = size_t(env_par);
     if (par < 1) par = 1;
     if (par > 1) c->helpers.ensure(par - 1);
     static const bool trace = std::getenv("LORAB200_TRACE") != nullptr;
@@ -281,7 +317,7 @@ int h2d_copy(lorab200_ctx *c, void *dst, const void *src, size_t bytes, cudaStre
         char *ring = static_cast<char *>(c->h_ring);
         const std::function<void(size_t)> fill = [&](size_t i) {
             const size_t o = i * kRingSlotBytes, len = left - o < kRingSlotBytes ? left - o : kRingSlotBytes;
-            std::memcpy(ring + size_t(slot[i]) * kRingSlotBytes, from + o, len);
+            slot_fill(ring + size_t(slot[i]) * kRingSlotBytes, from + o, len);
         };
         if (n_slots > 1) c->helpers.parallel(n_slots, fill);
         else fill(0);

@@ -34,6 +34,18 @@ namespace lorab200 {
 #define RXPROF(i) do { } while (0)
 #endif
 
+// Cold paths kept out of line: the receiver kernel's hot loop should fit the instruction caches (a build
+// with everything inlined ran many-channel launches at half the speed).
+__device__ __noinline__ int fine_advance_cold(const FineWalkDev *fw, int x, unsigned long long n)
+{
+    return fine_advance_dev(*fw, x, n);
+}
+__device__ __noinline__ void fine_walk_make_cold(FineWalkDev *fw, FineWalk32 *fw32, int len, float d)
+{
+    *fw = fine_walk_make_dev(len, d);
+    *fw32 = fine_walk32_make(*fw);
+}
+
 template <int SF>
 struct RxBatchCfg {
     using C = FusedCfg<SF>;
@@ -67,6 +79,7 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
     __shared__ RxState st;
     __shared__ FineWalkDev fw;
     __shared__ FineWalk32 fw32;
+    __shared__ int s_spec_ok, s_spec_m;     // one-warp rounds: closed-form guess of the chunk starts allowed / its modulus
     __shared__ int s_after[K::BR];           // _fineTuneIndex after each window of the round (its last chunk's walk)
     __shared__ RawResult rawres[K::BR];
     __shared__ RxRoundRes res[K::BR];
@@ -121,7 +134,7 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
 
         // g^n(x) of the fine-tune recurrence: 32-bit region walk when the step allows it
         auto adv = [&](int x, unsigned long long n) -> int {
-            return (fw32.ok && n < (1ull << 28)) ? fine_advance32(fw32, x, unsigned(n)) : fine_advance_dev(fw, x, n);
+            return (fw32.ok && n < (1ull << 28)) ? fine_advance32(fw32, x, unsigned(n)) : fine_advance_cold(&fw, x, n);
         };
         // thread 0 plans a round: how many windows, under which state (shared s_* variables)
         auto plan = [&]() {
@@ -148,13 +161,14 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                 s_d = d;
                 s_walk = (d != 0.0f);
                 if (s_walk && d != s_fw_d) {
-                    fw = fine_walk_make_dev(p.fine_len, d);
+                    fine_walk_make_cold(&fw, &fw32, p.fine_len, d);
                     s_fw_d = d;
                     const bool kp_none = fw.Kp == 0x7fffffffffffffffll;
                     s_lin_ok = (fw.integer || kp_none) ? 1 : 0;
                     s_lin_step = int(fw.integer ? fw.D : fw.D + 1);
                     s_lin_lo = fw.integer ? 0 : int(fw.D + 1 > 0 ? fw.D + 1 : 0);
-                    fw32 = fine_walk32_make(fw);
+                    s_spec_ok = (s_lin_ok && s_lin_step != 0 && s_lin_step > -(1 << 17) && s_lin_step < (1 << 17)) ? 1 : 0;
+                    s_spec_m = (!fw.integer && s_lin_step > 0) ? p.fine_len + 1 : p.fine_len;
                 }
                 if (!s_walk) s_phasor = p.fine[s_x0];
             }
@@ -177,35 +191,72 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                 // ---- fine-tune indices of this thread's 16 pass-0 samples -----------------------------
                 int fidx[16];
                 if (walking) {
-                    int x = live ? adv(s_x0, (unsigned long long)k * N + 16ull * t) : 0;
                     const uint32_t fx = xbase + uint32_t(wsub) * C::FINE_WSTRIDE * 4u;
                     const uint32_t cbase = fx + uint32_t(fine_pad_dyn(16 * t)) * 4u;
-                    const int xe = x - 15 * s_lin_step;
-                    const bool linear = s_lin_ok && min(x, xe) >= s_lin_lo && max(x, xe) < p.fine_len;
+                    // walk this thread's 16-sample chunk from state x, park the 16 indices, return the state
+                    // after the chunk.  Inside the constant-step region of the recurrence (fine_walk.h) a step
+                    // is "minus step, then the reference's wrap"; everything else is the literal float step.
+                    auto chunk = [&](int x) -> int {
+                        const int xe = x - 15 * s_lin_step;
+                        const bool linear = s_lin_ok && min(x, xe) >= s_lin_lo && max(x, xe) < p.fine_len;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        int v[4];
-                        if (linear) {
+                        for (int q = 0; q < 4; ++q) {
+                            int v[4];
+                            if (linear) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) v[i] = x - (4 * q + i) * s_lin_step;
-                        } else {
+                                for (int i = 0; i < 4; ++i) v[i] = x - (4 * q + i) * s_lin_step;
+                            } else {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) { v[i] = x; x = fine_next(x, s_d, p.fine_len); }
+                                for (int i = 0; i < 4; ++i) {
+                                    v[i] = x;
+                                    if (s_lin_ok && x >= s_lin_lo) {
+                                        x -= s_lin_step;
+                                        if (x < 0) x += p.fine_len; else if (x >= p.fine_len) x -= p.fine_len;
+                                    } else {
+                                        x = fine_next(x, s_d, p.fine_len);
+                                    }
+                                }
+                            }
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + q * 16u),
+                                         "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
                         }
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + q * 16u),
-                                     "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
-                    }
-                    // the thread that walked the window's last chunk is one step from the index after the
-                    // window (what the state machine carries on, LoRaDemod.cpp:160-162 after N samples)
-                    if (live && t == G - 1) {
                         if (linear) {
-                            // all 16 states of the chunk are inside the constant-step region: the 16th step is
-                            // "minus step" too, then the reference's wrap
+                            // all 16 states of the chunk are inside the region: the 16th step is "minus step" too
                             x = x - 16 * s_lin_step;
                             if (x < 0) x += p.fine_len; else if (x >= p.fine_len) x -= p.fine_len;
                         }
-                        s_after[k] = x;
+                        return x;
+                    };
+                    const unsigned long long n0 = (unsigned long long)k * N + 16ull * t;   // samples before the chunk
+                    // One-warp rounds: every chunk of the round is walked by a lane of this warp, so a GUESS of
+                    // the chunk starts can be checked exactly -- lane 0 starts from the true state and every
+                    // chunk must end where the next lane started.  The guess: while the walk only meets the
+                    // constant-step region and the plain wrap, the state after n samples is
+                    // (x0 - n * step) mod M, M = len + 1 for a fractional positive step (the one literal step
+                    // per wrap of the table subtracts floor(d), not floor(d) + 1), M = len otherwise.  A failed
+                    // check (a state in the rounding band, index 0 / D, ...) takes the region walk (attempt 1).
+                    int xend = 0;
+                    const bool guess = (GROUP == 32) && s_solo && s_spec_ok;
+#pragma unroll 1
+                    for (int attempt = guess ? 0 : 1; attempt < 2; ++attempt) {
+                        int x;
+                        if (attempt == 0) {
+                            int m = (s_x0 - int(n0) * s_lin_step) % s_spec_m;
+                            if (m < 0) m += s_spec_m;
+                            x = live ? m : 0;
+                        } else {
+                            x = live ? adv(s_x0, n0) : 0;
+                        }
+                        xend = chunk(x);
+                        if (attempt == 0) {
+                            const int nx = __shfl_down_sync(0xffffffffu, x, 1);
+                            const bool has_succ = live && (t < G - 1 || k + 1 < nwin);
+                            if (__all_sync(0xffffffffu, !has_succ || xend == nx)) break;
+                        }
                     }
+                    // the thread that walked the window's last chunk holds the index after the window (what the
+                    // state machine carries on, LoRaDemod.cpp:160-162 after N samples)
+                    if (live && t == G - 1) s_after[k] = xend;
                     group_sync<GROUP>(grp);
                     const uint32_t gb = fx + uint32_t(fine_pad_dyn(E == 1 ? t : 2 * t)) * 4u;
                     if constexpr (E == 1) {
@@ -407,27 +458,26 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                     s_force2 = 1;
                 }
         };
+        // One call site each for compute / walk / plan (the kernel is ~90 KB of code; a second inlined copy
+        // for the one-warp rounds made many-channel launches fetch-bound).  A one-warp (solo) stretch: warp 0
+        // iterates alone with warp-level syncs, the other warps wait at the barrier at the top of the loop.
         if (tid == 0) plan();
         for (;;) {
             __syncthreads();
             if (!s_go) break;
-            if (s_solo) {
-                if (warp_u == 0) {
-                    do {
-                        compute();
-                        __syncwarp();
-                        if (lane == 0) { walk(); RXPROF(6); plan(); RXPROF(7); }
+            const bool solo = s_solo != 0;
+            if (solo && warp_u != 0) continue;
+            bool again;
+            do {
+                compute();
+                if (solo) __syncwarp(); else __syncthreads();
+                if (tid == 0) { walk(); RXPROF(6); plan(); RXPROF(7); }
 #ifdef LORAB200_RX_PROF
-                        if (lane == 0) prof_rounds++;
+                if (tid == 0 && solo) prof_rounds++;
 #endif
-                        __syncwarp();
-                    } while (s_go && s_solo);
-                }
-                continue;
-            }
-            compute();
-            __syncthreads();
-            if (tid == 0) { walk(); plan(); }
+                again = false;
+                if (solo) { __syncwarp(); again = s_go && s_solo; }
+            } while (again);
         }
         if (st.phase == RX_DATASYMBOLS && unsigned(npk) < p.max_packets)
             for (int k = tid; k < st.sym_count; k += K::CTA)
