@@ -658,6 +658,27 @@ def main():
                  "records_bit_exact": bool(host_out[pick].tobytes() == exp.tobytes()),
                  "decoded_equals_sent": float(np.mean(host_out["index"] == syms[last].cpu().numpy()))}
 
+    # the host->device copy of a step's input ALONE (same page-locked buffer, no kernel, no D2H), every rank
+    # copying at the same time: the ceiling the e2e leg sits under (one PCIe gen5 x16 link per GPU, and at
+    # N = 8 the host's memory system feeding eight of them)
+    src_t = torch.from_numpy(host_bufs[0].reshape(-1).view(np.float32))
+    dst_t = torch.empty(src_t.shape, dtype=torch.float32, device=device)
+    for _ in range(2):
+        dst_t.copy_(src_t, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n_copies = 10
+    t0 = time.perf_counter()
+    for _ in range(n_copies):
+        dst_t.copy_(src_t, non_blocking=True)
+    torch.cuda.synchronize()
+    tc = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    h2d_only_gbs = step_bytes * n_copies / float(tc.item()) / 1e9
+    del dst_t, src_t
+
     # the same call with ordinary (pageable) host memory, as a framework's default buffers are:
     # the library stages it through its own pinned ring (filled by a few helper threads)
     pageable = np.array(host_bufs[0])
@@ -728,6 +749,8 @@ def main():
                 "d2h_bytes_per_step": nw * 32, "steps": Ke, "check": e2e_check,
                 "symbols_ok": bool(e2e_check["indices_bit_exact"]),
                 "pageable_input_value": e2e_pageable,
+                "h2d_copy_alone_gbs_per_gpu": h2d_only_gbs,
+                "h2d_gbs_in_e2e_per_gpu": e2e_value / world * 1e6 * (8 * n) / 1e9,
                 "api": "lorab200_demod_host (host buffers from lorab200_alloc_pinned; H2D + kernel + D2H + host finalise per step)"},
         "gpu_launches": int(launches_per_graph),
         "roofline": roof,

@@ -1190,7 +1190,33 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     if ((n_windows + cw - 1) / cw > 64) cw = (n_windows + 63) / 64;
     // a walking fine-tune index uses per-context scratch for its prefix (fine_prefix.cuh): one chunk
     if (fine && fine->step != 0.0f) cw = n_windows;
-    const size_t n_chunks = (n_windows + cw - 1) / cw;
+    // Chunk boundaries.  Full chunks of cw windows, then a tapered tail (cw/2, cw/4, cw/8, cw/8): when the last
+    // copy has landed only the last chunk's kernel, D2H and host finalisation remain, and during that tail
+    // the PCIe link idles until the caller's next batch -- a short last chunk keeps it short.
+    size_t cb[65];
+    size_t n_chunks = 0;
+    {
+        size_t w = 0;
+        const bool taper = !(fine && fine->step != 0.0f) && cw >= 64 && n_windows >= 4 * cw && (n_windows + cw - 1) / cw <= 60;
+        cb[0] = 0;
+        while (w < n_windows) {
+            size_t step = cw;
+            const size_t left = n_windows - w;
+            if (taper && left <= cw) {
+                static const size_t div[4] = {2, 4, 8, 8};
+                for (int q = 0; q < 4 && w < n_windows; ++q) {
+                    size_t sub = (cw / div[q] + 7) / 8 * 8;   // (multiples of 8 windows: tiles never straddle chunks)
+                    if (q == 3 || sub > n_windows - w) sub = n_windows - w;
+                    w += sub;
+                    cb[++n_chunks] = w;
+                }
+                break;
+            }
+            if (step > left) step = left;
+            w += step;
+            cb[++n_chunks] = w;
+        }
+    }
     const float2 *h_iq = reinterpret_cast<const float2 *>(iq);
     float2 *d_iq = static_cast<float2 *>(c->d_iq.p);
     RawResult *d_raw = static_cast<RawResult *>(c->d_raw.p);
@@ -1199,7 +1225,7 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     size_t copied_to = 0; // samples [0, copied_to) are already on the device
     for (size_t k = 0; k < n_chunks; ++k) {
         cudaStream_t s = (k & 1) ? c->stream2 : c->stream;
-        const size_t w0 = k * cw, w1 = (w0 + cw < n_windows) ? w0 + cw : n_windows, nw = w1 - w0;
+        const size_t w0 = cb[k], w1 = cb[k + 1], nw = w1 - w0;
         const size_t s0 = w0 * stride_samples, s1 = (w1 - 1) * stride_samples + n; // sample range of the chunk
         const size_t from = s0 > copied_to ? s0 : copied_to;                        // skip what an earlier chunk brought
         if (s1 > from) {
@@ -1227,25 +1253,25 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     // soon as its results have landed, while later chunks are still in flight.  Large
     // batches split the chunks over a few threads so this stays hidden behind the H2D copy.
     std::atomic<int> ferr_code{int(cudaSuccess)};
-    // finalisation tasks are slices of a chunk (<= ftask windows) so that the last chunk's tail is
-    // spread over the helper threads too
-    size_t ftask = 1024;
-    if (ftask > cw) ftask = cw;
-    const size_t per_chunk = (cw + ftask - 1) / ftask;
+    // finalisation tasks are slices of a chunk: <= 1024 windows, <= 128 in the last two chunks so that the
+    // tail after the last copy is spread evenly over the helper threads
+    struct FTask { uint32_t chunk; size_t p0, p1; };
+    std::vector<FTask> tasks;
+    for (size_t k = 0; k < n_chunks; ++k) {
+        const size_t ft = (k + 2 >= n_chunks && n_chunks >= 4) ? 128 : 1024;
+        for (size_t p0 = cb[k]; p0 < cb[k + 1]; p0 += ft)
+            tasks.push_back({uint32_t(k), p0, p0 + ft < cb[k + 1] ? p0 + ft : cb[k + 1]});
+    }
     const std::function<void(size_t)> finish = [&](size_t task) {
-        const size_t k = task / per_chunk, sub = task % per_chunk;
-        const size_t c0 = k * cw, c1 = (c0 + cw < n_windows) ? c0 + cw : n_windows;
-        const size_t p0 = c0 + sub * ftask;
-        if (p0 >= c1) return;
-        const size_t p1 = (p0 + ftask < c1) ? p0 + ftask : c1;
-        cudaError_t e = cudaEventSynchronize(c->chunk_done[k % 64]);
+        const FTask &t = tasks[task];
+        cudaError_t e = cudaEventSynchronize(c->chunk_done[t.chunk % 64]);
         if (e != cudaSuccess) { ferr_code = int(e); return; }
-        finalize_host(h_raw + p0, p1 - p0, c->pscale, out + p0);
+        finalize_host(h_raw + t.p0, t.p1 - t.p0, c->pscale, out + t.p0);
     };
-    const size_t n_tasks = n_chunks * per_chunk;
+    const size_t n_tasks = tasks.size();
     if (n_windows >= 16384 && n_chunks >= 4) {
         size_t n_thr = host_threads() / 4;
-        if (n_thr > 8) n_thr = 8;
+        if (n_thr > 16) n_thr = 16;   // (the tail after the last chunk is one pass of these threads)
         if (n_thr > n_tasks) n_thr = n_tasks;
         if (n_thr < 2) n_thr = 2;
         c->helpers.ensure(n_thr - 1);

@@ -31,16 +31,27 @@ for sf in a.sf:
     buf = torch.from_numpy(one).cuda().repeat(a.channels, 1).contiguous()
     for thresh in (-30.0, -5.0):
         ref = loopback.receive(sf, 4, one, use_b200=False, debug_ports=True, mtu=a.mtu, thresh=thresh)
-        r = d.rx_dev(buf, thresh=thresh, mtu=a.mtu, max_packets=2 * a.packets + 4)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
-        e0.record()
-        for _ in range(reps):
+        # A launch with one busy warp per CTA is a light load: after the CPU-side reference run above the GPU
+        # has idled and its clocks take tens of milliseconds to come back (the same binary on the same data
+        # measured anywhere between 3.8 and 11 ms per call when timed cold).  Warm up for >= 60 ms of back to
+        # back calls, then take the best of several timed calls.
+        import time
+        t_end = time.perf_counter() + 0.06
+        while True:
             r = d.rx_dev(buf, thresh=thresh, mtu=a.mtu, max_packets=2 * a.packets + 4)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
+            torch.cuda.synchronize()
+            if time.perf_counter() > t_end:
+                break
+        reps = 7
+        times = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = d.rx_dev(buf, thresh=thresh, mtu=a.mtu, max_packets=2 * a.packets + 4)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = min(times)
         npk = r["n_packets"].cpu().numpy()
         info = r["info"][0].cpu().numpy()
         same = int(npk[0]) == len(ref["symbols"]) and all(
@@ -48,7 +59,7 @@ for sf in a.sf:
         print(json.dumps({
             "sf": sf, "thresh_db": thresh, "channels": a.channels, "samples_per_channel": int(one.size),
             "packets_per_channel": int(npk[0]), "identical_to_reference_block": bool(same and (npk == npk[0]).all()),
-            "gpu_ms": ms, "gpu_aggregate_Msamples_per_s": a.channels * one.size / ms / 1e3,
+            "gpu_ms": ms, "gpu_ms_all": [round(t, 3) for t in times], "gpu_aggregate_Msamples_per_s": a.channels * one.size / ms / 1e3,
             "gpu_per_channel_Msamples_per_s": one.size / ms / 1e3,
             "reference_block_1thread_Msamples_per_s": one.size / ref["seconds"] / 1e6,
         }), flush=True)
