@@ -111,7 +111,9 @@ def make_config(args):
                f"({nbuf * step_bytes >> 20} MiB > 3x L2), so every step streams from HBM") if not args.l2_resident
         else f"ONE {step_bytes >> 20} MiB buffer reused every step (L2-resident, --l2-resident)",
         "timing": "K steps captured in one CUDA graph (programmatic dependent launch between steps, "
-                  "LORAB200_FLAG_INPUT_STABLE), CUDA events on the launching stream",
+                  "LORAB200_FLAG_INPUT_STABLE), CUDA events on the launching stream around exactly those K "
+                  "steps; after the barrier + synchronize the same graph runs untimed for ~4 ms directly in "
+                  "front of the timed replay (a B200 that idled at the barrier runs its next ~2 ms 5 % slower)",
         "fine_step": args.fine_step,
         "sharding": "windows block-partitioned per rank, no data-path collective",
     }
@@ -400,14 +402,17 @@ def time_graph(torch, dist, world, device, launch, K, W, demod, sampler=None, su
     # continuous work to get back to its steady speed, so a 20-step (0.3 ms) region timed right after
     # the interpreter's pauses (NVML queries, graph capture) would time that ramp, not the kernel.
     # ~4 ms is far below the ~70 ms after which the software power cap sets in (see `sustained`).
+    # With several ranks the barrier itself is such a gap (a rank that arrives first idles until the last one
+    # does: the 8-GPU line measured 15.5 us per step against 14.4 on 1-2 GPUs while the longer sweep
+    # entries scaled at 0.998-1.0), so the pre-load is enqueued AFTER the barrier + synchronize, directly in
+    # front of the timed graph on the same stream: the events still bracket exactly K steps.
     n_pre = 0 if est_ms >= 8.0 else max(1, min(200, int(np.ceil(4.0 / max(est_ms, 1e-3)))))
-    with torch.cuda.stream(stream):
-        for _ in range(n_pre):
-            graph.replay()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     with torch.cuda.stream(stream):
+        for _ in range(n_pre):
+            graph.replay()
         e0.record(stream)
         graph.replay()
         e1.record(stream)

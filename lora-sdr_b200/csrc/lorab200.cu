@@ -1270,8 +1270,8 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     };
     const size_t n_tasks = tasks.size();
     if (n_windows >= 16384 && n_chunks >= 4) {
-        size_t n_thr = host_threads() / 4;
-        if (n_thr > 16) n_thr = 16;   // (the tail after the last chunk is one pass of these threads)
+        size_t n_thr = host_threads() / 2;   // (a rank bound to its share of a NUMA node has ~16 CPUs)
+        if (n_thr > 16) n_thr = 16;          // (the tail after the last chunk is one pass of these threads)
         if (n_thr > n_tasks) n_thr = n_tasks;
         if (n_thr < 2) n_thr = 2;
         c->helpers.ensure(n_thr - 1);
