@@ -15,3 +15,5 @@ for sf in 7 10 12; do
 done
 ncu --set full --clock-control none --import-source on -k regex:demod_fused -s 4 -c 1 -f -o gpurun_out/prof_walk_sf7 \
     tools/kbench --lib $L --sf 7 --windows 65536 --steps 4 --reps 1 --fine-step 1.28 > gpurun_out/ncu_walk.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:rx_batch -s 2 -c 1 -f -o gpurun_out/prof_rx_sf7 \
+    python tools/rx_bench.py --channels 256 --sf 7 > gpurun_out/ncu_rx.log 2>&1

@@ -119,6 +119,27 @@ def main():
               f"{summ['lane_instructions_per_sample']} lane-instr/sample, issue "
               f"{m.get('smsp__issue_active.avg.pct_of_peak_sustained_active')}%")
     tp.write_text(json.dumps(traffic, indent=1))
+    # the other captures of tools/profile.sh: the walking fine-tune form of the fused kernel and the receiver kernel
+    extras = [
+        ("prof_walk_sf7.ncu-rep", f"{tag}_ncu_walk_sf7.json", 65536 * 128,
+         "ncu --set full, one launch of demod_fused_kernel<SF=7, FINE_ORBIT> (65536 windows, fine step 1.28): the walking "
+         "fine-tune index evaluated from the orbit of the walk, phasors gathered from the L2-resident table"),
+        ("prof_rx_sf7.ncu-rep", f"{tag}_ncu_rx_sf7.json", None,
+         "ncu --set full, one launch of rx_batch_kernel<SF=7> over 256 channels (tools/rx_bench.py, squelch -30 dB: the "
+         "never-squelched stream, one busy warp per CTA): a latency chain, not a throughput kernel"),
+    ]
+    for name, out_name, samples, what in extras:
+        rep = SRC / name
+        if not rep.exists():
+            continue
+        m = raw_metrics(rep)
+        mix, total, stalls = source_mix(rep)
+        summ = {"what": what, "metrics": m, "warp_instructions_executed": total,
+                "instruction_mix_top": mix, "stall_reasons_pct_of_samples": stalls}
+        if samples:
+            summ["lane_instructions_per_sample"] = round(total * 32 / samples, 2)
+        (OUT / out_name).write_text(json.dumps(summ, indent=1))
+        print(f"{name}: {m.get('gpu__time_duration.sum')} us, issue {m.get('smsp__issue_active.avg.pct_of_peak_sustained_active')}%")
     lc = SRC / "launches_sf7.csv"
     if lc.exists():
         shutil.copy(lc, OUT / f"{tag}_launches_sf7.csv")
