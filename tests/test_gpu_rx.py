@@ -87,6 +87,47 @@ def test_rx_dev_matches_the_reference_block(lib, cuda_ok, sf, thresh, flags):
 
 
 @needs_chain
+@pytest.mark.parametrize("sf", [7, 8, 10])
+def test_rx_dev_with_carrier_offsets(lib, cuda_ok, sf):
+    """Streams with a carrier frequency offset (a fraction of a bin up to a few bins, both signs): the
+    preamble then leaves _finefreqError far from zero, positive and negative, and the fine-tune index walks
+    the table by tens to hundreds of entries per sample with a wrap every few chunks -- the regime of the
+    32-bit region walk, the verified closed-form chunk starts of the one-warp rounds (rx_batch.cuh) and the
+    in-region fast step.  Same packets, symbols, error signal and samples consumed as the reference block."""
+    import torch
+    rng = np.random.default_rng(900 + sf)
+    n = 1 << sf
+    cfos = [0.31, -0.27, 1.7, -2.4, 0.07, -0.9, 3.3, -0.05]
+    streams = []
+    for c, cfo in enumerate(cfos):
+        pk = [bytes(rng.integers(0, 256, int(rng.integers(6, 24)), dtype=np.uint8)) for _ in range(2)]
+        iq = loopback.transmit(sf, 4, pk, padding=40, sigma=0.03, seed=700 * sf + c)
+        lead = int(rng.integers(0, 2 << sf))
+        noise = (rng.standard_normal(lead) + 1j * rng.standard_normal(lead)).astype(np.complex64) * np.float32(0.03)
+        x = np.concatenate([noise, iq])
+        rot = np.exp(2j * np.pi * cfo / n * np.arange(x.size)).astype(np.complex64)
+        streams.append((x * rot).astype(np.complex64))
+    m = max(s.size for s in streams)
+    buf = np.zeros((len(streams), m), np.complex64)
+    for c, s_ in enumerate(streams):
+        buf[c, : s_.size] = s_
+    d = lib.Demod(sf)
+    for thresh in (-30.0, -6.0):
+        r = d.rx_dev(torch.from_numpy(buf).cuda(), thresh=thresh, mtu=64, max_packets=16)
+        torch.cuda.synchronize()
+        assert d.last_kernel.startswith("rx_sf")
+        for c in range(len(streams)):
+            ref = loopback.receive(sf, 4, buf[c], use_b200=False, debug_ports=True, mtu=64, thresh=thresh)
+            got = _unpack(r, c)
+            assert len(got) == len(ref["symbols"]), f"cfo {cfos[c]} thresh {thresh}: {len(got)} packets vs {len(ref['symbols'])}"
+            for p_, g in enumerate(got):
+                assert np.array_equal(g["symbols"], ref["symbols"][p_]), f"cfo {cfos[c]} packet {p_}"
+                assert g["error"] == ref["error"][p_]
+            assert int(r["consumed"][c]) == ref["samples"], f"cfo {cfos[c]}: consumed"
+    d.close()
+
+
+@needs_chain
 @pytest.mark.parametrize("sf", [7, 9])
 def test_iq_to_payload_bytes_entirely_on_the_device(lib, cuda_ok, sf):
     """lorab200_rx_dev -> lorab200_decode_dev: IQ streams in HBM to payload bytes in two launches; the
