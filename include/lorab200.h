@@ -37,7 +37,8 @@
 extern "C" {
 #endif
 
-#define LORAB200_ABI_VERSION 2 /* 2: lorab200_rx_state / lorab200_rx_packet carry the raw peak and total; lorab200_rx_host */
+#define LORAB200_ABI_VERSION 3 /* 2: lorab200_rx_state / lorab200_rx_packet carry the raw peak and total; lorab200_rx_host
+                                * 3: lorab200_preamble_search_dev (additive) */
 
 typedef struct lorab200_ctx lorab200_ctx;
 
@@ -286,6 +287,37 @@ int lorab200_rx_dev(lorab200_ctx *ctx, const void *iq_dev, size_t n_channels, si
                     lorab200_rx_state *state_dev, int16_t *partial_dev, int16_t *symbols_dev,
                     lorab200_rx_packet *info_dev, int32_t *n_packets_dev, uint64_t *consumed_dev,
                     size_t max_packets, void *cuda_stream);
+
+/*
+ * Preamble search over all candidate offsets (behavioural, not bit, parity).
+ * The reference acquires a frame by hunting: every un-squelched window consumes N - value samples to
+ * re-time the stream (LoRaDemod.cpp:179-237, :219), one dependent window after the other.  This call
+ * demodulates the windows at offsets 0, S, 2S, ... of ONE stream (S = stride_samples; an even S takes the
+ * fused kernel) against the up-chirp table in a single launch and reports, in stream order, every maximal
+ * run of at least min_windows consecutive windows whose snr (power - power_avg, the reference's squelch
+ * quantity, :173-174) is >= thresh_db and whose phase = (offset - index) mod N moves by at most one bin
+ * from window to window: inside a train of identical up-chirps a window delta samples past a chirp
+ * boundary dechirps to bin delta, so that phase is constant over a preamble whatever the offsets.
+ *   found_dev    [max_found] records (device); n_found_dev receives the number of runs found, which may
+ *                exceed max_found (only the first max_found, in stream order, are written)
+ *   offset       first window of the run;  aligned = offset + N - index of that window: where the
+ *                reference's re-timing (:219) would put the next window
+ *   windows      windows in the run (measured up to 65536);  snr_db mean over the run;  power_db its peak
+ * A receiver can start its state machine (lorab200_rx_dev with a zeroed state) at `aligned` instead of
+ * walking there.  Uses per-context scratch (16 B + 1 B per window).  Asynchronous on cuda_stream.
+ */
+typedef struct lorab200_preamble {
+    uint64_t offset;
+    uint64_t aligned;
+    int32_t phase;
+    int32_t windows;
+    float snr_db;
+    float power_db;
+} lorab200_preamble;
+
+int lorab200_preamble_search_dev(lorab200_ctx *ctx, const void *iq_dev, size_t n_samples, size_t stride_samples,
+                                 float thresh_db, int min_windows, lorab200_preamble *found_dev,
+                                 int32_t *n_found_dev, uint32_t max_found, void *cuda_stream);
 
 /*
  * The same receiver for HOST buffers -- what a block's work() calls (LoRaDemod.cpp:145-327 for the whole

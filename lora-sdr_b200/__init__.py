@@ -37,6 +37,10 @@ RESULT_DTYPE = np.dtype(
     [("index", "<i4"), ("power", "<f4"), ("power_avg", "<f4"), ("f_index", "<f4")]
 )
 
+PREAMBLE_DTYPE = np.dtype(   # lorab200_preamble
+    [("offset", "<u8"), ("aligned", "<u8"), ("phase", "<i4"), ("windows", "<i4"), ("snr_db", "<f4"), ("power_db", "<f4")]
+)
+
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -53,6 +57,7 @@ EXPORTS = [
     "lorab200_kernel_launches", "lorab200_last_kernel", "lorab200_alloc_pinned",
     "lorab200_free_pinned", "lorab200_is_pinned", "lorab200_table_len", "lorab200_build_table", "lorab200_fine_advance",
     "lorab200_demod_multi_dev", "lorab200_mod_samples", "lorab200_mod_dev", "lorab200_decode_dev", "lorab200_rx_dev", "lorab200_rx_host", "lorab200_encode_host", "lorab200_decode_host", "lorab200_mod_host", "lorab200_encode_dev", "lorab200_encode_symbols",
+    "lorab200_preamble_search_dev",
 ]
 
 
@@ -145,6 +150,7 @@ def load_library() -> C.CDLL:
     L.lorab200_decode_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, vp, vp]
     L.lorab200_rx_dev.argtypes = [vp, vp, sz, sz, sz, C.c_uint, C.c_float, sz, vp, vp, vp, vp, vp, vp, sz, vp]
     L.lorab200_rx_host.argtypes = [vp, vp, sz, sz, C.c_uint, C.c_float, sz, vp, vp, vp, vp, vp, vp, sz]
+    L.lorab200_preamble_search_dev.argtypes = [vp, vp, sz, sz, C.c_float, C.c_int, vp, vp, C.c_uint32, vp]
     L.lorab200_encode_dev.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, vp, vp]
     L.lorab200_encode_symbols.restype = sz
     L.lorab200_encode_symbols.argtypes = [C.c_int, vp, sz]
@@ -349,6 +355,29 @@ class Demod:
                                     C.c_void_p(stream))
         self._check(st, "rx_dev")
         return dict(symbols=symbols, info=info, n_packets=n_packets, consumed=consumed, state=state)
+
+    # ---- preamble search over all candidate offsets ---------------------------
+    def preamble_search(self, iq, stride=None, thresh=-3.0, min_windows=8, max_found=256, stream=None):
+        """iq: CUDA complex64 tensor [samples] (one stream).  Demodulates the windows at offsets 0, stride, ...
+        in one launch and returns (records, n_found): records = numpy structured array (PREAMBLE_DTYPE) of the
+        first min(n_found, max_found) preambles in stream order."""
+        import torch
+
+        assert iq.is_cuda and iq.is_contiguous() and iq.dim() == 1
+        stride = (self.n // 4) if stride is None else int(stride)
+        dev = iq.device
+        found = torch.zeros((max(1, max_found), PREAMBLE_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        n_found = torch.zeros(1, dtype=torch.int32, device=dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        st = self.L.lorab200_preamble_search_dev(self.ctx, C.c_void_p(iq.data_ptr()), iq.numel(), stride,
+                                                 C.c_float(thresh), int(min_windows), C.c_void_p(found.data_ptr()),
+                                                 C.c_void_p(n_found.data_ptr()), int(max_found), C.c_void_p(stream))
+        self._check(st, "preamble_search_dev")
+        torch.cuda.synchronize(dev)
+        nf = int(n_found.item())
+        rec = np.frombuffer(found.cpu().numpy().tobytes(), dtype=PREAMBLE_DTYPE)[: min(nf, max_found)].copy()
+        return rec, nf
 
     def rx_host(self, iq_list, sync=0x12, thresh=-30.0, mtu=256, max_packets=16, state=None):
         """Host-buffer twin of :meth:`rx_dev`: iq_list = one contiguous complex64 numpy array per channel, all of

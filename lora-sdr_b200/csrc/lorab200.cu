@@ -36,6 +36,7 @@
 #include "decode.cuh"
 #include "rx_kernel.cuh"
 #include "rx_batch.cuh"
+#include "acquire.cuh"
 #include "finalize.h"
 #include "tables.h"
 
@@ -171,6 +172,7 @@ struct lorab200_ctx {
     void *h_rx = nullptr;    // pinned: lorab200_rx_host's state / packets block (read and written by the kernel)
     size_t h_rx_cap = 0;
     DevBuf d_rx_iq;          // lorab200_rx_host: the channels' IQ on the device
+    DevBuf d_acq_res, d_acq_valid, d_acq_tiles;   // lorab200_preamble_search_dev scratch
     DevBuf d_hio[4];         // host-buffer twins of encode / decode / mod: inputs and outputs on the device
     // pageable callers (a framework's ordinary port buffers): large H2D copies are staged through
     // a ring of pinned slots so that the PCIe copy of one slot overlaps the memcpy into the next
@@ -693,6 +695,7 @@ void lorab200_destroy(lorab200_ctx *c)
     if (c->h_rx) cudaFreeHost(c->h_rx);
     if (c->d_rx_iq.p) cudaFree(c->d_rx_iq.p);
     for (DevBuf &b : c->d_hio) if (b.p) cudaFree(b.p);
+    for (DevBuf *b : {&c->d_acq_res, &c->d_acq_valid, &c->d_acq_tiles}) if (b->p) cudaFree(b->p);
     if (c->h_ring) cudaFreeHost(c->h_ring);
     for (auto &ev : c->ring_free) if (ev) cudaEventDestroy(ev);
     (void)cudaGetLastError();
@@ -1283,6 +1286,58 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
     if (ferr != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "cudaEventSynchronize(chunk)", ferr);
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream2));
+    return LORAB200_OK;
+}
+
+int lorab200_preamble_search_dev(lorab200_ctx *c, const void *iq_dev, size_t n_samples, size_t stride_samples,
+                                 float thresh_db, int min_windows, lorab200_preamble *found_dev,
+                                 int32_t *n_found_dev, uint32_t max_found, void *cuda_stream)
+{
+    if (!c) return LORAB200_ERR_INVALID;
+    c->err.clear();
+    if (!n_found_dev) return fail(c, LORAB200_ERR_INVALID, "n_found_dev is null");
+    if (max_found > 0 && !found_dev) return fail(c, LORAB200_ERR_INVALID, "found_dev is null");
+    if (stride_samples == 0) return fail(c, LORAB200_ERR_INVALID, "stride_samples must be > 0");
+    if (min_windows < 1) return fail(c, LORAB200_ERR_INVALID, "min_windows must be >= 1");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const size_t n = c->n;
+    if (n_samples < n) {
+        CU_TRY(c, cudaMemsetAsync(n_found_dev, 0, sizeof(int32_t), s));
+        return LORAB200_OK;
+    }
+    if (!iq_dev) return fail(c, LORAB200_ERR_INVALID, "iq pointer is null");
+    const size_t n_win = (n_samples - n) / stride_samples + 1;
+    if (n_win >= (size_t(1) << 31)) return fail(c, LORAB200_ERR_UNSUPPORTED, "too many windows in one call");
+    const size_t n_tiles = (n_win + kAcqTile - 1) / kAcqTile;
+    int st;
+    if ((st = ensure_dev(c, c->d_acq_res, n_win * sizeof(lorab200_result)))) return st;
+    if ((st = ensure_dev(c, c->d_acq_valid, n_win))) return st;
+    if ((st = ensure_dev(c, c->d_acq_tiles, 2 * n_tiles * sizeof(int)))) return st;
+    lorab200_result *res = static_cast<lorab200_result *>(c->d_acq_res.p);
+    // every candidate offset in one launch of the demod kernel (windows overlap: the batch is read from L2)
+    if ((st = run_demod(c, iq_dev, n_win, stride_samples, LORAB200_TABLE_UP, nullptr, res, nullptr, nullptr, nullptr, s))) return st;
+    AcqParams p{};
+    p.res = res;
+    p.n_win = n_win;
+    p.stride = stride_samples;
+    p.n = int(n);
+    p.thresh = thresh_db;
+    p.min_windows = min_windows;
+    p.valid = static_cast<unsigned char *>(c->d_acq_valid.p);
+    p.tile_count = static_cast<int *>(c->d_acq_tiles.p);
+    p.tile_base = p.tile_count + n_tiles;
+    p.n_tiles = unsigned(n_tiles);
+    p.found = found_dev;
+    p.n_found = n_found_dev;
+    p.max_found = max_found;
+    const unsigned grid = unsigned(n_tiles < size_t(c->sm_count) * 8 ? n_tiles : size_t(c->sm_count) * 8);
+    acq_mark_kernel<<<grid, kAcqTile, 0, s>>>(p);
+    acq_scan_kernel<<<1, 1024, 0, s>>>(p);
+    acq_emit_kernel<<<grid, kAcqTile, 0, s>>>(p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(c, LORAB200_ERR_CUDA, "preamble search launch", e);
+    c->launches += 3;
     return LORAB200_OK;
 }
 

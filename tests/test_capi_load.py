@@ -28,7 +28,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_abi_version_and_strerror(lib):
     L = lib.load_library()
-    assert L.lorab200_abi_version() == 2      # 2: rx state / packet structs carry the raw peak and total; lorab200_rx_host
+    assert L.lorab200_abi_version() == 3      # 2: rx state / packet structs carry the raw peak and total; lorab200_rx_host; 3: preamble search
     assert L.lorab200_strerror(0) == b"ok"
     assert L.lorab200_strerror(-1) == b"invalid argument"
     assert L.lorab200_table_len(7, lib.TABLE_UP) == 128

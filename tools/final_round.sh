@@ -25,6 +25,7 @@ python tools/block_bench.py --sf 7 10 12 --packets 16 --repeat 4 > gpurun_out/bl
 python tools/block_bench.py --sf 7 10 12 --packets 16 --repeat 4 --thresh -5 > gpurun_out/block_bench_thresh-5.jsonl 2>/dev/null
 python tools/rx_bench.py --channels 256 > gpurun_out/rx_bench_256.jsonl 2>/dev/null
 python tools/rx_bench.py --channels 1024 --sf 7 10 > gpurun_out/rx_bench_1024.jsonl 2>/dev/null
+python tools/acquire_bench.py > gpurun_out/acquire_bench.jsonl 2>/dev/null
 python tools/mod_bench.py > gpurun_out/mod_bench.jsonl 2> gpurun_out/mod_bench.err
 python tools/call_latency.py > gpurun_out/call_latency.txt 2>&1
 compute-sanitizer --tool racecheck python tools/sanitize_small.py > gpurun_out/racecheck.log 2>&1; tail -2 gpurun_out/racecheck.log
