@@ -351,7 +351,7 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
         const uint32_t w0 = tile * WPT;
         uint32_t nw = n_windows - w0;
         if (nw > WPT) nw = WPT;
-        const uint32_t bytes = nw * N * 8u;
+        const uint32_t bytes = (WPT > 1 && p.stride < N) ? uint32_t((nw - 1) * p.stride + N) * 8u : nw * N * 8u;
         mbar_expect_tx(bar0 + s * 8, bytes);
         const float2 *src;
         if constexpr (MULTI) {
@@ -361,6 +361,10 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
             src = p.iq + size_t(w0) * p.stride;
         }
         if (WPT == 1 || p.stride == N) {
+            tma_load_1d(gbase + s * C::STAGE_BYTES, src, bytes, bar0 + s * 8);
+        } else if (p.stride < N) {
+            // overlapping windows (a sliding search): the tile's windows share samples, ONE copy of the span
+            // they cover; window i of the tile then starts stride samples (not N) after window i - 1 in the stage
             tma_load_1d(gbase + s * C::STAGE_BYTES, src, bytes, bar0 + s * 8);
         } else {
             for (uint32_t i = 0; i < nw; ++i)
@@ -426,7 +430,8 @@ demod_fused_kernel(const DemodParams p, const Pass0Tw p0tw, const float2 fine_ph
 
     // per-thread addresses (bytes)
     // pass-0 input: i(e, c) = ilow(e) + (N/R0)*c,  ilow = t (E==1) or ehi*2G + 2t + e0
-    const uint32_t in_off = (uint32_t(wsub) * N + uint32_t(E == 1 ? t : 2 * t)) * 8u;
+    const uint32_t wstep = (WPT > 1 && p.stride < N) ? uint32_t(p.stride) : uint32_t(N);   // window pitch inside a stage
+    const uint32_t in_off = (uint32_t(wsub) * wstep + uint32_t(E == 1 ? t : 2 * t)) * 8u;
     const uint32_t chirp_off = uint32_t(E == 1 ? t : 2 * t) * 8u;
     const uint32_t wx = xbase + uint32_t(wsub) * C::WSTRIDE * 8u; // this window's exchange area
     // pass-0 scatter: j = x(c) | digit_rev(ilow(e)) << B0.  The e part of ilow lands in bits of j that the
