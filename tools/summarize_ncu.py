@@ -153,6 +153,15 @@ def main():
                 pass
         tot = sum(by.values()) or 1
         lines = [f"{k}: {v/1e3:.1f} us total, {100*v/tot:.1f}% of all profiled launches" for k, v in by.most_common(8)]
+        ours = sorted(float(r[-1].replace(",", "")) for r in rows if "lorab200" in r[4])
+        if ours:
+            full = [v for v in ours if v >= 0.75 * ours[-1]]      # the 65 536-window launches (the others are the
+            lines.insert(0,                                       # parity check and the 8 192-window e2e chunks)
+                         f"lorab200 launches in the list: {len(ours)}, of which {len(full)} full-batch (65 536 windows) with a "
+                         f"per-launch duration under ncu (serialised, cold, no PDL overlap) of median {full[len(full)//2]/1e3:.2f} us, "
+                         f"min {full[0]/1e3:.2f} us; the rest are the parity check and the host-buffer leg's 8 192-window chunks.  "
+                         "Inside bench.py's timed region every launch is this kernel (gpu_launches == steps); the at:: kernels "
+                         "below build the synthetic input before it.")
         (OUT / f"{tag}_launches_sf7_summary.txt").write_text("\n".join(lines) + "\n")
         print("\n".join(lines[:4]))
 
