@@ -151,6 +151,8 @@ struct lorab200_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;          // second lane of the host-buffer pipeline
+    cudaStream_t stream_h2d = nullptr;       // all host->device chunk copies of the pipeline, back to back
+    cudaEvent_t h2d_done[64] = {};           // chunk k's samples are on the device
     cudaEvent_t chunk_done[64] = {};          // D2H-complete events of the in-flight chunks
     std::string err;
     std::string last_kernel;
@@ -644,8 +646,11 @@ int lorab200_create(lorab200_ctx **out, int device, int sf, uint32_t flags)
         c->sm_count = prop.multiProcessorCount;
         if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { st = fail(nullptr, LORAB200_ERR_CUDA, "cudaStreamCreate", e); break; }
         if ((e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess) { st = fail(nullptr, LORAB200_ERR_CUDA, "cudaStreamCreate", e); break; }
+        if ((e = cudaStreamCreateWithFlags(&c->stream_h2d, cudaStreamNonBlocking)) != cudaSuccess) { st = fail(nullptr, LORAB200_ERR_CUDA, "cudaStreamCreate", e); break; }
         for (auto &ev : c->chunk_done)
             if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) break;
+        for (auto &ev : c->h2d_done)
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fine_done, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->aux_done, cudaEventDisableTiming);
         for (auto &ev : c->ring_free)
@@ -685,6 +690,8 @@ void lorab200_destroy(lorab200_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    if (c->stream_h2d) { cudaStreamSynchronize(c->stream_h2d); cudaStreamDestroy(c->stream_h2d); }
+    for (auto &ev : c->h2d_done) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->chunk_done) if (ev) cudaEventDestroy(ev);
     for (auto &t : c->d_table) if (t) cudaFree(t);
     for (DevBuf *b : {&c->d_iq, &c->d_raw, &c->d_fft, &c->d_dec, &c->d_fine_t, &c->d_fine_p[0], &c->d_fine_p[1], &c->d_fine_x, &c->d_mod_phase, &c->d_mod_phasor, &c->d_dec_scratch}) if (b->p) cudaFree(b->p);
@@ -1231,20 +1238,23 @@ int lorab200_demod_host(lorab200_ctx *c, const float *iq, size_t n_windows, size
         const size_t w0 = cb[k], w1 = cb[k + 1], nw = w1 - w0;
         const size_t s0 = w0 * stride_samples, s1 = (w1 - 1) * stride_samples + n; // sample range of the chunk
         const size_t from = s0 > copied_to ? s0 : copied_to;                        // skip what an earlier chunk brought
+        // Every chunk's copy goes on ONE stream, so that the copy engine runs them back to back (with the copies
+        // on the two compute streams each one started a few microseconds after the previous lane's dependency
+        // resolved); the chunk's kernel waits for its copy -- and, the copies being in order, for everything an
+        // earlier chunk brought (stride < N: the head of this chunk).
         if (s1 > from) {
-            // stride < N: the head of this chunk was copied by chunk k-1 on the other
-            // stream; order this stream after that chunk
-            if (k > 0 && from > s0) CU_TRY(c, cudaStreamWaitEvent(s, c->chunk_done[(k - 1) % 64], 0));
-            if ((st = h2d_copy(c, d_iq + from, h_iq + from, (s1 - from) * sizeof(float2), s, pageable))) {
-                cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2);
+            if ((st = h2d_copy(c, d_iq + from, h_iq + from, (s1 - from) * sizeof(float2), c->stream_h2d, pageable))) {
+                cudaStreamSynchronize(c->stream_h2d); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2);
                 return st;
             }
             copied_to = s1;
         }
+        CU_TRY(c, cudaEventRecord(c->h2d_done[k % 64], c->stream_h2d));
+        CU_TRY(c, cudaStreamWaitEvent(s, c->h2d_done[k % 64], 0));
         st = run_demod(c, d_iq + s0, nw, stride_samples, table, fine, nullptr, d_raw + w0,
                        fft ? static_cast<float2 *>(c->d_fft.p) + w0 * n : nullptr,
                        dec ? static_cast<float2 *>(c->d_dec.p) + w0 * n : nullptr, s);
-        if (st) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); return st; }
+        if (st) { cudaStreamSynchronize(c->stream_h2d); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); return st; }
         CU_TRY(c, cudaMemcpyAsync(h_raw + w0, d_raw + w0, nw * sizeof(RawResult), cudaMemcpyDeviceToHost, s));
         if (fft) CU_TRY(c, cudaMemcpyAsync(reinterpret_cast<float2 *>(fft) + w0 * n, static_cast<float2 *>(c->d_fft.p) + w0 * n,
                                            nw * n * sizeof(float2), cudaMemcpyDeviceToHost, s));
