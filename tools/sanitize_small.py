@@ -45,3 +45,20 @@ for sf in (7, 9, 10, 12):
             assert int(r["n_packets"].min()) >= 1, (sf, flags, thresh)
         d.close()
     print("rx sf", sf, "ok", flush=True)
+
+# the preamble search (sliding windows through the fused kernel + the mark / scan / emit kernels)
+for sf in (7, 8, 10):
+    n = 1 << sf
+    d = m.Demod(sf)
+    payloads = torch.from_numpy(rng.integers(0, 256, (1, 9), dtype=np.uint8)).cuda()
+    syms, nsy = d.encode_dev(payloads, rdd=4, crc=True)
+    iq = d.mod_dev(syms, padding=20, ampl=1.0, mode=m.MOD_IDEAL)[0]
+    g = torch.Generator("cuda").manual_seed(50 + sf)
+    lead = 0.05 * torch.view_as_complex(torch.randn((n + 3, 2), device=iq.device, generator=g))
+    stream = torch.cat([lead, iq, lead, iq]).contiguous()
+    stream = stream + 0.05 * torch.view_as_complex(torch.randn((stream.numel(), 2), device=iq.device, generator=g))
+    for div in (4, 8):
+        rec, nf = d.preamble_search(stream, stride=n // div, thresh=-3.0, min_windows=4 * div)
+        assert nf == 2, (sf, div, nf)
+    d.close()
+    print("search sf", sf, "ok", flush=True)
