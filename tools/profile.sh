@@ -13,7 +13,9 @@ for sf in 7 10 12; do
       tools/kbench --lib $L --sf $sf --windows $w --steps 4 --reps 1 > gpurun_out/ncu_sf$sf.log 2>&1
   tail -1 gpurun_out/ncu_sf$sf.log | cut -c1-80
 done
-ncu --set full --clock-control none --import-source on -k regex:demod_fused -s 4 -c 1 -f -o gpurun_out/prof_walk_sf7 \
+# (no imported source for the two secondary captures: the summaries only need the SASS page, and five reports
+#  with source exceed the 64 MiB gpurun brings back)
+ncu --set full --clock-control none -k regex:demod_fused -s 4 -c 1 -f -o gpurun_out/prof_walk_sf7 \
     tools/kbench --lib $L --sf 7 --windows 65536 --steps 4 --reps 1 --fine-step 1.28 > gpurun_out/ncu_walk.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:rx_batch -s 2 -c 1 -f -o gpurun_out/prof_rx_sf7 \
+ncu --set full --clock-control none -k regex:rx_batch -s 2 -c 1 -f -o gpurun_out/prof_rx_sf7 \
     python tools/rx_bench.py --channels 256 --sf 7 > gpurun_out/ncu_rx.log 2>&1
