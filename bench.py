@@ -722,8 +722,9 @@ def main():
         del pinned, host_bufs, keep, pageable, bufs, segs, out
         torch.cuda.empty_cache()
         common = (torch, dist, m, world, rank, device, local)
-        for s_sf, s_w, s_steps in ((10, 16384, 100), (12, 16384, 40)):
-            if s_sf != sf:
+        # BASELINE configs[2]: "SF sweep 7-12, 16 384 windows each" (the headline above is configs[1], SF7 x 65 536)
+        for s_sf, s_w, s_steps in ((7, 16384, 200), (8, 16384, 200), (9, 16384, 100), (10, 16384, 100), (11, 16384, 60), (12, 16384, 40)):
+            if s_sf != sf or s_w != nw:
                 sweep.append(sweep_entry(*common, s_sf, s_w, s_steps, None, peak, f"sf{s_sf}"))
         # the fine-tune multiply of the reference's steady-state data path (LoRaDemod.cpp:157-166):
         # constant index (_finefreqError == 0) and an index walking 1.28 entries per sample
