@@ -279,7 +279,9 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
                 RXPROF(1);   // walking index
                 // the next step starts somewhere in (off, off + 2N]: whatever it is, it needs samples up to 3N
                 // ahead; pull the part this round does not read into L1 while it computes
-                if (s_solo && k == 0 && t * 16 < N)
+                // (the one-warp rounds of SF7 / SF8 and the one-window passes of SF12, where it measured +7 %; at SF9 /
+                //  SF10 the same prefetch in the CTA-wide sequential rounds measured -4 ... -6 % and is left out)
+                if ((s_solo || (B == 1 && nwin <= 2)) && k == 0 && t * 16 < N && off + 3ull * N + 16 <= p.n_samples)
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(win + 2 * N + t * 16));
                 // ---- load (global, 8-byte aligned), dechirp, fine-tune multiply (LoRaDemod.cpp:157-159) ----
                 c64 r[16];
