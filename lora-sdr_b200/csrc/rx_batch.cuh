@@ -25,10 +25,12 @@
 
 namespace lorab200 {
 
-// -DLORAB200_RX_PROF: cycle accounting of the one-warp (solo) rounds, printed by the kernel (a tuning aid,
-// not part of the product build)
+// -DLORAB200_RX_PROF=1: cycle accounting of the one-warp (solo) rounds; =2: of every round of at most two windows
+// (the sequential phases at any SF), as thread 0 sees them.  Printed by the kernel: a tuning aid, not part of
+// the product build.  (prof_on is latched when a round starts, so that the time of rounds that are not accounted
+// is not attributed to the next marker.)
 #ifdef LORAB200_RX_PROF
-#define RXPROF(i) do { if (s_solo && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); \
+#define RXPROF(i) do { if (prof_on && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); \
                        prof_acc[i] += t_ - prof_last; prof_last = t_; } } while (0)
 #else
 #define RXPROF(i) do { } while (0)
@@ -89,7 +91,8 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
     __shared__ float2 s_phasor;
 #ifdef LORAB200_RX_PROF
     __shared__ long long prof_acc[12], prof_last, prof_rounds;
-    if (threadIdx.x == 0) { for (int i = 0; i < 12; ++i) prof_acc[i] = 0; prof_rounds = 0; asm volatile("mov.u64 %0, %%clock64;" : "=l"(prof_last) :: "memory"); }
+    __shared__ int prof_on;
+    if (threadIdx.x == 0) { for (int i = 0; i < 12; ++i) prof_acc[i] = 0; prof_rounds = 0; prof_on = 0; asm volatile("mov.u64 %0, %%clock64;" : "=l"(prof_last) :: "memory"); }
 #endif
 
     const int tid = threadIdx.x;
@@ -471,11 +474,18 @@ __global__ void __launch_bounds__(256, 2) rx_batch_kernel(const RxParams p, cons
             if (solo && warp_u != 0) continue;
             bool again;
             do {
+#ifdef LORAB200_RX_PROF
+                if (tid == 0) {
+                    prof_on = (s_solo || (LORAB200_RX_PROF > 1 && s_nwin <= 2)) ? 1 : 0;
+                    asm volatile("mov.u64 %0, %%clock64;" : "=l"(prof_last) :: "memory");
+                }
+                if (solo) __syncwarp(); else __syncthreads();
+#endif
                 compute();
                 if (solo) __syncwarp(); else __syncthreads();
                 if (tid == 0) { walk(); RXPROF(6); plan(); RXPROF(7); }
 #ifdef LORAB200_RX_PROF
-                if (tid == 0 && solo) prof_rounds++;
+                if (tid == 0 && prof_on) prof_rounds++;
 #endif
                 again = false;
                 if (solo) { __syncwarp(); again = s_go && s_solo; }
